@@ -1,0 +1,192 @@
+// Client side of the engine (host only): secret keys, evaluation keys, encryption, phases.
+// Mirrors what the reference obtains from circuit.keygen()/encrypt()/decrypt()
+// (/root/reference/matrix_inversion/main.py:177, qfloat_matrix_inversion.py:1032,1035).
+// Deterministic: every random word is a pure function of (seed, stream, counter).
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/bmi_tfhe.h"
+#include "field.cuh"
+#include "host_common.h"
+
+namespace {
+
+inline u64 mix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+struct Rng {
+    u64 base;
+    Rng(u64 seed, u64 stream) : base(mix64(mix64(seed) ^ stream)) {}
+    u64 raw(u64 ctr) const { return mix64(base ^ ctr); }
+    u64 field(u64 ctr) const { u64 r = raw(ctr); return r >= BMI_P ? r - BMI_P : r; }
+    u64 bit(u64 ctr) const { return raw(ctr) >> 63; }
+    u64 gauss(u64 ctr, double sigma) const {
+        const u64 r1 = raw(2 * ctr), r2 = raw(2 * ctr + 1);
+        const double u1 = (double)((r1 >> 11) + 1) * 0x1.0p-53, u2 = (double)(r2 >> 11) * 0x1.0p-53;
+        const double z = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * u2);
+        return from_i64((i64)std::llround(z * sigma));
+    }
+};
+enum { ST_LWE_KEY = 1, ST_GLWE_KEY = 2, ST_BSK_MASK = 3, ST_BSK_NOISE = 4, ST_KSK_MASK = 5, ST_KSK_NOISE = 6,
+       ST_ENC_MASK = 7, ST_ENC_NOISE = 8 };
+
+// host negacyclic transform (merged-twiddle butterflies), used only to multiply masks by key polynomials
+struct HostNtt {
+    int N, L;
+    std::vector<u64> tw, twi;
+    u64 ninv;
+    explicit HostNtt(int n) : N(n), L(0) {
+        while ((1 << L) < N) L++;
+        bmi_host::twiddles(N, tw, twi);
+        ninv = fpow((u64)N, BMI_P - 2);
+    }
+    void fwd(u64* a) const {
+        int t = N;
+        for (int m = 1; m < N; m <<= 1) {
+            t >>= 1;
+            for (int i = 0; i < m; i++) {
+                const u64 w = tw[m + i];
+                u64 *x = a + 2 * i * t, *y = x + t;
+                for (int j = 0; j < t; j++) { const u64 u = x[j], v = fmul(y[j], w); x[j] = fadd(u, v); y[j] = fsub(u, v); }
+            }
+        }
+    }
+    void inv(u64* a) const {
+        int t = 1;
+        for (int m = N >> 1; m >= 1; m >>= 1) {
+            for (int i = 0; i < m; i++) {
+                const u64 w = twi[m + i];
+                u64 *x = a + 2 * i * t, *y = x + t;
+                for (int j = 0; j < t; j++) { const u64 u = x[j], v = y[j]; x[j] = fadd(u, v); y[j] = fmul(fsub(u, v), w); }
+            }
+            t <<= 1;
+        }
+        for (int j = 0; j < N; j++) a[j] = fmul(a[j], ninv);
+    }
+};
+
+template <class F>
+void parallel_for(int64_t count, int threads, F f) {
+    threads = std::max(1, std::min<int>(threads, (int)std::min<int64_t>(count, 256)));
+    if (threads == 1) { f(0, count); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(f, count * t / threads, count * (t + 1) / threads);
+    for (auto& th : pool) th.join();
+}
+
+bool check(const bmi_params* p) {
+    if (!p || p->n < 1 || p->k < 1 || p->N < 2 || (p->N & (p->N - 1)) || p->bsk_l < 1 || p->ksk_l < 1 ||
+        p->bsk_bl < 1 || p->ksk_bl < 1 || p->bsk_bl * p->bsk_l > 63 || p->ksk_bl * p->ksk_l > 63) {
+        bmi_host::set_error("invalid bmi_params");
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmi_keygen_lwe(const bmi_params* p, uint64_t seed, uint64_t* s) {
+    if (!check(p) || !s) return BMI_EINVAL;
+    Rng r(seed, ST_LWE_KEY);
+    for (int i = 0; i < p->n; i++) s[i] = r.bit(i);
+    return BMI_OK;
+}
+
+int bmi_keygen_glwe(const bmi_params* p, uint64_t seed, uint64_t* S) {
+    if (!check(p) || !S) return BMI_EINVAL;
+    Rng r(seed, ST_GLWE_KEY);
+    for (int i = 0; i < p->k * p->N; i++) S[i] = r.bit(i);
+    return BMI_OK;
+}
+
+int bmi_keygen_bsk(const bmi_params* p, uint64_t seed, const uint64_t* s, const uint64_t* S, uint64_t* bsk, int threads) {
+    if (!check(p) || !s || !S || !bsk) return BMI_EINVAL;
+    const int k = p->k, N = p->N, l = p->bsk_l, rows = (k + 1) * l;
+    const HostNtt ntt(N);
+    std::vector<u64> Shat((size_t)k * N);
+    for (int m = 0; m < k; m++) {
+        std::memcpy(&Shat[(size_t)m * N], S + (size_t)m * N, sizeof(u64) * N);
+        ntt.fwd(&Shat[(size_t)m * N]);
+    }
+    const Rng rm(seed, ST_BSK_MASK), rn(seed, ST_BSK_NOISE);
+    parallel_for((int64_t)p->n * rows, threads, [&](int64_t lo, int64_t hi) {
+        std::vector<u64> sum(N), tmp(N);
+        for (int64_t id = lo; id < hi; id++) {
+            u64* row = bsk + (size_t)id * (k + 1) * N;
+            u64* body = row + (size_t)k * N;
+            std::fill(sum.begin(), sum.end(), 0);
+            for (int m = 0; m < k; m++) {
+                u64* A = row + (size_t)m * N;
+                for (int t = 0; t < N; t++) A[t] = rm.field(((u64)id * k + m) * N + t);
+                std::memcpy(tmp.data(), A, sizeof(u64) * N);
+                ntt.fwd(tmp.data());
+                for (int t = 0; t < N; t++) sum[t] = fadd(sum[t], fmul(tmp[t], Shat[(size_t)m * N + t]));
+            }
+            ntt.inv(sum.data());
+            for (int t = 0; t < N; t++) body[t] = fadd(sum[t], rn.gauss((u64)id * N + t, p->glwe_sigma));
+            const int i = (int)(id / rows), r = (int)(id % rows), c = r / l, j = r % l + 1;
+            if (s[i]) row[(size_t)c * N] = fadd(row[(size_t)c * N], 1ULL << (64 - j * p->bsk_bl));
+        }
+    });
+    return BMI_OK;
+}
+
+int bmi_keygen_ksk(const bmi_params* p, uint64_t seed, const uint64_t* s, const uint64_t* S, uint64_t* ksk, int threads) {
+    if (!check(p) || !s || !S || !ksk) return BMI_EINVAL;
+    const int n = p->n, l = p->ksk_l;
+    const Rng rm(seed, ST_KSK_MASK), rn(seed, ST_KSK_NOISE);
+    parallel_for((int64_t)p->k * p->N * l, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t id = lo; id < hi; id++) {
+            u64* ct = ksk + (size_t)id * (n + 1);
+            u64 b = rn.gauss((u64)id, p->lwe_sigma);
+            for (int t = 0; t < n; t++) {
+                ct[t] = rm.field((u64)id * n + t);
+                if (s[t]) b = fadd(b, ct[t]);
+            }
+            const int i = (int)(id / l), j = (int)(id % l) + 1;
+            if (S[i]) b = fadd(b, 1ULL << (64 - j * p->ksk_bl));
+            ct[n] = b;
+        }
+    });
+    return BMI_OK;
+}
+
+int bmi_lwe_encrypt(const bmi_params* p, uint64_t seed, uint64_t ct_index0, const uint64_t* S, const uint64_t* pt,
+                    int64_t count, uint64_t* out) {
+    if (!check(p) || !S || !pt || !out || count < 0) return BMI_EINVAL;
+    const int dim = p->k * p->N;
+    const Rng rm(seed, ST_ENC_MASK), rn(seed, ST_ENC_NOISE);
+    parallel_for(count, 8, [&](int64_t lo, int64_t hi) {
+        for (int64_t q = lo; q < hi; q++) {
+            const u64 id = ct_index0 + (u64)q;
+            u64* ct = out + (size_t)q * (dim + 1);
+            u64 b = fadd(rn.gauss(id, p->glwe_sigma), pt[q] % BMI_P);
+            for (int t = 0; t < dim; t++) {
+                ct[t] = rm.field(id * dim + t);
+                if (S[t]) b = fadd(b, ct[t]);
+            }
+            ct[dim] = b;
+        }
+    });
+    return BMI_OK;
+}
+
+int bmi_lwe_phase(const uint64_t* key, int32_t dim, const uint64_t* ct, int64_t count, uint64_t* phase) {
+    if (!key || !ct || !phase || dim < 1 || count < 0) { bmi_host::set_error("invalid argument"); return BMI_EINVAL; }
+    for (int64_t q = 0; q < count; q++) {
+        const u64* c = ct + (size_t)q * (dim + 1);
+        u64 ph = c[dim];
+        for (int t = 0; t < dim; t++) if (key[t]) ph = fsub(ph, c[t]);
+        phase[q] = ph;
+    }
+    return BMI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// Server side of the engine: device context, key upload/conversion, kernel launchers, C ABI.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bmi_tfhe.h"
+#include "host_common.h"
+#include "kernels.cuh"
+
+namespace bmi_host {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace bmi_host
+using bmi_host::set_error;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+            return BMI_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+struct bmi_ctx {
+    bmi_params p;
+    int device, logN;
+    u64 ninv;
+    u64 *d_tw = nullptr, *d_twi = nullptr, *d_bsk = nullptr, *d_ksk = nullptr, *d_luts = nullptr;
+    int n_luts = 0;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // scratch for the host-buffer convenience path
+    u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
+    int *w_idx = nullptr, *w_lut = nullptr;
+    int64_t w_cap = 0;
+};
+
+namespace {
+
+size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
+
+template <int L>
+int setup_attrs(const bmi_ctx* c) {
+    CK(cudaFuncSetAttribute(pbs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
+    CK(cudaFuncSetAttribute(bsk_convert_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    CK(cudaFuncSetAttribute(polymul_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    return BMI_OK;
+}
+
+template <int L>
+int launch_convert(bmi_ctx* c, const u64* src, u64* dst, int64_t polys, cudaStream_t st) {
+    bsk_convert_kernel<L><<<(unsigned)polys, NttCfg<L>::T, (1 << L) * 8, st>>>(src, dst, c->d_tw, c->ninv);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+template <int L>
+int launch_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) {
+    const int64_t total = (int64_t)a.njobs * a.batch;
+    const unsigned grid = (unsigned)std::min<int64_t>(total, 1 << 20);
+    pbs_kernel<L><<<grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+template <int L>
+int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, cudaStream_t st) {
+    polymul_kernel<L><<<count, NttCfg<L>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+#define DISPATCH_L(c, expr)                                  \
+    switch ((c)->logN) {                                     \
+        case 10: { constexpr int L = 10; return expr; }      \
+        case 11: { constexpr int L = 11; return expr; }      \
+        case 12: { constexpr int L = 12; return expr; }      \
+        case 13: { constexpr int L = 13; return expr; }      \
+        default: set_error("unsupported polynomial size"); return BMI_EINVAL; \
+    }
+
+int do_setup(bmi_ctx* c) { DISPATCH_L(c, setup_attrs<L>(c)); }
+int do_convert(bmi_ctx* c, const u64* s, u64* d, int64_t polys, cudaStream_t st) { DISPATCH_L(c, launch_convert<L>(c, s, d, polys, st)); }
+int do_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) { DISPATCH_L(c, launch_pbs<L>(c, a, st)); }
+int do_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* o, int n, cudaStream_t st) { DISPATCH_L(c, launch_polymul<L>(c, a, b, o, n, st)); }
+
+int ensure_scratch(bmi_ctx* c, int64_t count) {
+    if (count <= c->w_cap) return BMI_OK;
+    cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
+    c->w_cap = 0;
+    const size_t big = (size_t)c->p.k * c->p.N + 1;
+    CK(cudaMalloc(&c->w_in, count * big * 8));
+    CK(cudaMalloc(&c->w_small, count * (size_t)(c->p.n + 1) * 8));
+    CK(cudaMalloc(&c->w_out, count * big * 8));
+    CK(cudaMalloc(&c->w_idx, count * sizeof(int)));
+    CK(cudaMalloc(&c->w_lut, count * sizeof(int)));
+    std::vector<int> iota(count);
+    for (int64_t i = 0; i < count; i++) iota[i] = (int)i;
+    CK(cudaMemcpy(c->w_idx, iota.data(), count * sizeof(int), cudaMemcpyHostToDevice));
+    c->w_cap = count;
+    return BMI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bmi_version(void) { return "bmi_tfhe 0.1 (sm_100a)"; }
+const char* bmi_last_error(void) { return bmi_host::g_err.c_str(); }
+
+int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
+    if (!p || !out) { set_error("null argument"); return BMI_EINVAL; }
+    if (p->k != 1) { set_error("kernels support GLWE dimension k == 1 only"); return BMI_EINVAL; }
+    int logN = 0;
+    while ((1 << logN) < p->N) logN++;
+    if ((1 << logN) != p->N || logN < 10 || logN > 13) { set_error("polynomial size must be 1024..8192"); return BMI_EINVAL; }
+    if (p->bsk_bl * p->bsk_l > 63 || p->ksk_bl * p->ksk_l > 63 || p->ksk_bl > 30 || p->n < 1 || p->n > 4096) {
+        set_error("unsupported decomposition / dimension");
+        return BMI_EINVAL;
+    }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return BMI_ECUDA; }
+    CK(cudaSetDevice(device));
+    bmi_ctx* c = new bmi_ctx();
+    c->p = *p; c->device = device; c->logN = logN;
+    c->ninv = fpow((u64)p->N, BMI_P - 2);
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+    std::vector<u64> tw, twi;
+    bmi_host::twiddles(p->N, tw, twi);
+    CK(cudaMalloc(&c->d_tw, p->N * 8));
+    CK(cudaMalloc(&c->d_twi, p->N * 8));
+    CK(cudaMemcpy(c->d_tw, tw.data(), p->N * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_twi, twi.data(), p->N * 8, cudaMemcpyHostToDevice));
+    int rc = do_setup(c);
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return BMI_OK;
+}
+
+int bmi_ctx_destroy(bmi_ctx* c) {
+    if (!c) return BMI_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk); cudaFree(c->d_ksk); cudaFree(c->d_luts);
+    cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
+    delete c;
+    return BMI_OK;
+}
+
+int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
+    if (!c || !h_bsk) { set_error("null argument"); return BMI_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    const int64_t polys = (int64_t)c->p.n * 2 * c->p.bsk_l * 2;
+    const size_t bytes = (size_t)polys * c->p.N * 8;
+    if (!c->d_bsk) CK(cudaMalloc(&c->d_bsk, bytes));
+    // upload in slices through a bounded staging buffer, converting slice by slice
+    const int64_t slice = std::min<int64_t>(polys, 4096);
+    u64* stage = nullptr;
+    CK(cudaMalloc(&stage, (size_t)slice * c->p.N * 8));
+    for (int64_t p0 = 0; p0 < polys; p0 += slice) {
+        const int64_t cnt = std::min(slice, polys - p0);
+        CK(cudaMemcpy(stage, h_bsk + (size_t)p0 * c->p.N, (size_t)cnt * c->p.N * 8, cudaMemcpyHostToDevice));
+        int rc = do_convert(c, stage, c->d_bsk + (size_t)p0 * c->p.N, cnt, 0);
+        if (rc) { cudaFree(stage); return rc; }
+        CK(cudaDeviceSynchronize());
+    }
+    cudaFree(stage);
+    return BMI_OK;
+}
+
+int bmi_ctx_load_ksk(bmi_ctx* c, const uint64_t* h_ksk) {
+    if (!c || !h_ksk) { set_error("null argument"); return BMI_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->p.k * c->p.N * c->p.ksk_l * (c->p.n + 1) * 8;
+    if (!c->d_ksk) CK(cudaMalloc(&c->d_ksk, bytes));
+    CK(cudaMemcpy(c->d_ksk, h_ksk, bytes, cudaMemcpyHostToDevice));
+    return BMI_OK;
+}
+
+int bmi_ctx_load_luts(bmi_ctx* c, const uint64_t* h_luts, int32_t n_luts) {
+    if (!c || !h_luts || n_luts < 1) { set_error("invalid argument"); return BMI_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->d_luts);
+    c->d_luts = nullptr;
+    CK(cudaMalloc(&c->d_luts, (size_t)n_luts * c->p.N * 8));
+    CK(cudaMemcpy(c->d_luts, h_luts, (size_t)n_luts * c->p.N * 8, cudaMemcpyHostToDevice));
+    c->n_luts = n_luts;
+    return BMI_OK;
+}
+
+int64_t bmi_ctx_launch_count(const bmi_ctx* c) { return c ? c->launches : 0; }
+
+int bmi_lincomb(bmi_ctx* c, const uint64_t* d_vals, const int32_t* d_row_ptr, const int32_t* d_idx, const uint64_t* d_coef,
+                const uint64_t* d_konst, uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
+    if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (njobs == 0) return BMI_OK;
+    const int W = c->p.k * c->p.N + 1;
+    dim3 grid((unsigned)((int64_t)njobs * batch), (W + 2047) / 2048);
+    lincomb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_vals, d_row_ptr, d_idx, d_coef, d_konst, d_out, W, batch);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t count, void* stream) {
+    if (!c || count < 0) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (!c->d_ksk) { set_error("keyswitch key not loaded"); return BMI_ESTATE; }
+    if (count == 0) return BMI_OK;
+    dim3 grid((c->p.n + 1 + KS_COLS - 1) / KS_COLS, (unsigned)((count + KS_JT - 1) / KS_JT));
+    const size_t smem = (size_t)KS_CHUNK * c->p.ksk_l * KS_JT * sizeof(int);
+    keyswitch_kernel<<<grid, KS_COLS, smem, (cudaStream_t)stream>>>(d_in, c->d_ksk, d_out, (int)count, c->p.k * c->p.N, c->p.n,
+                                                                   c->p.ksk_bl, c->p.ksk_l);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+int bmi_pbs(bmi_ctx* c, const uint64_t* d_small, const int32_t* d_job_in, const int32_t* d_job_lut, const int32_t* d_job_out,
+            uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
+    if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (!c->d_bsk || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
+    if (njobs == 0) return BMI_OK;
+    PbsArgs a;
+    a.bsk_hat = c->d_bsk; a.tw = c->d_tw; a.twi = c->d_twi; a.luts = c->d_luts; a.small = d_small;
+    a.job_in = d_job_in; a.job_lut = d_job_lut; a.job_out = d_job_out; a.out = d_out;
+    a.njobs = njobs; a.batch = batch; a.n = c->p.n; a.bl = c->p.bsk_bl; a.l = c->p.bsk_l;
+    return do_pbs(c, a, (cudaStream_t)stream);
+}
+
+int bmi_ks_pbs_host(bmi_ctx* c, const uint64_t* h_in, const int32_t* h_lut_idx, uint64_t* h_out, int64_t count) {
+    if (!c || !h_in || !h_lut_idx || !h_out || count < 0) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (count == 0) return BMI_OK;
+    CK(cudaSetDevice(c->device));
+    for (int64_t q = 0; q < count; q++)
+        if (h_lut_idx[q] < 0 || h_lut_idx[q] >= c->n_luts) { set_error("LUT index out of range"); return BMI_EINVAL; }
+    int rc = ensure_scratch(c, count);
+    if (rc) return rc;
+    const size_t big = (size_t)c->p.k * c->p.N + 1;
+    CK(cudaMemcpyAsync(c->w_in, h_in, count * big * 8, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(c->w_lut, h_lut_idx, count * sizeof(int), cudaMemcpyHostToDevice, 0));
+    if ((rc = bmi_keyswitch(c, c->w_in, c->w_small, count, nullptr))) return rc;
+    if ((rc = bmi_pbs(c, c->w_small, c->w_idx, c->w_lut, c->w_idx, c->w_out, (int)count, 1, nullptr))) return rc;
+    CK(cudaMemcpyAsync(h_out, c->w_out, count * big * 8, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return BMI_OK;
+}
+
+int bmi_polymul_host(bmi_ctx* c, const uint64_t* h_a, const uint64_t* h_b, uint64_t* h_c, int32_t count) {
+    if (!c || !h_a || !h_b || !h_c || count < 1) { set_error("invalid argument"); return BMI_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)count * c->p.N * 8;
+    u64 *a = nullptr, *b = nullptr, *o = nullptr;
+    CK(cudaMalloc(&a, bytes)); CK(cudaMalloc(&b, bytes)); CK(cudaMalloc(&o, bytes));
+    CK(cudaMemcpy(a, h_a, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(b, h_b, bytes, cudaMemcpyHostToDevice));
+    int rc = do_polymul(c, a, b, o, count, 0);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(h_c, o, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = BMI_ECUDA; }
+    }
+    cudaFree(a); cudaFree(b); cudaFree(o);
+    return rc;
+}
+
+}  // extern "C"

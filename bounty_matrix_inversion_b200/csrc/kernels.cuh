@@ -1,0 +1,224 @@
+// Device kernels of the TFHE hot path (sm_100a).  One CTA bootstraps one ciphertext.
+#pragma once
+#include "ntt.cuh"
+
+struct PbsArgs {
+    const u64* __restrict__ bsk_hat;   // [n][2l][2][16][T]  transform domain, x 1/N
+    const u64* __restrict__ tw;        // [N] psi^brv(i)
+    const u64* __restrict__ twi;       // [N] psi^-brv(i)
+    const u64* __restrict__ luts;      // [n_luts][N]
+    const u64* __restrict__ small;     // [rows][n+1] keyswitched inputs
+    const int* __restrict__ job_in;    // [njobs] row (before batch expansion) into small
+    const int* __restrict__ job_lut;   // [njobs]
+    const int* __restrict__ job_out;   // [njobs] row (before batch expansion) into out
+    u64* __restrict__ out;             // [rows][N+1] big-key LWE
+    int njobs, batch;
+    int n, bl, l;
+};
+
+// ----------------------------------------------------------------------------
+// bootstrapping-key conversion: standard-domain polynomial -> kernel-native layout
+template <int L>
+__global__ void __launch_bounds__(NttCfg<L>::T) bsk_convert_kernel(const u64* __restrict__ src, u64* __restrict__ dst,
+                                                                   const u64* __restrict__ tw, u64 ninv) {
+    using C = NttCfg<L>;
+    extern __shared__ u64 smem[];
+    const int tid = threadIdx.x;
+    const u64* s = src + (size_t)blockIdx.x * C::N;
+    u64* d = dst + (size_t)blockIdx.x * C::N;
+    u64 x[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = s[q * C::T + tid];
+    ntt_forward<L>(x, smem, tw, tid);
+#pragma unroll
+    for (int q = 0; q < 16; q++) d[q * C::T + tid] = fmul(x[q], ninv);
+}
+
+// c = a * b mod (X^N + 1): exercises forward, pointwise and inverse transforms (self-test entry)
+template <int L>
+__global__ void __launch_bounds__(NttCfg<L>::T) polymul_kernel(const u64* __restrict__ a, const u64* __restrict__ b,
+                                                               u64* __restrict__ c, const u64* __restrict__ tw,
+                                                               const u64* __restrict__ twi, u64 ninv) {
+    using C = NttCfg<L>;
+    extern __shared__ u64 smem[];
+    const int tid = threadIdx.x;
+    const size_t off = (size_t)blockIdx.x * C::N;
+    u64 x[16], y[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) { x[q] = a[off + q * C::T + tid]; y[q] = b[off + q * C::T + tid]; }
+    ntt_forward<L>(x, smem, tw, tid);
+    ntt_forward<L>(y, smem, tw, tid);
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = fmul(fmul(x[q], y[q]), ninv);
+    ntt_inverse<L>(x, smem, twi, tid);
+#pragma unroll
+    for (int q = 0; q < 16; q++) c[off + q * C::T + tid] = x[q];
+}
+
+// ----------------------------------------------------------------------------
+// programmable bootstrap: modulus switch -> blind rotation -> sample extraction
+template <int L>
+__global__ void __launch_bounds__(NttCfg<L>::T, 1) pbs_kernel(const PbsArgs a) {
+    using C = NttCfg<L>;
+    constexpr int N = C::N, T = C::T;
+    extern __shared__ u64 smem[];
+    u64* acc = smem;                  // [2][N]: mask polynomial, body polynomial
+    u64* buf = smem + 2 * N;          // [N] transform exchange buffer (swizzled)
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N);   // [n] switched mask
+    const int tid = threadIdx.x;
+    const int n = a.n, bl = a.bl, l = a.l, tot = bl * l;
+
+    for (int f = blockIdx.x; f < a.njobs * a.batch; f += gridDim.x) {
+        const int q0 = f / a.batch, b0 = f - q0 * a.batch;
+        const u64* in = a.small + ((size_t)a.job_in[q0] * a.batch + b0) * (n + 1);
+        const u64* lut = a.luts + (size_t)a.job_lut[q0] * N;
+        u64* out = a.out + ((size_t)a.job_out[q0] * a.batch + b0) * (N + 1);
+
+        __syncthreads();   // previous job fully written out
+        for (int i = tid; i < n; i += T) rot[i] = (unsigned short)modswitch(in[i], L);
+        {   // acc = (0, X^{-b~} * lut)
+            const u32 r0 = (2 * N - modswitch(in[n], L)) & (2 * N - 1);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int idx = q * T + tid;
+                const u32 u = (idx + 2 * N - r0) & (2 * N - 1);
+                acc[idx] = 0;
+                acc[N + idx] = u < N ? lut[u] : fneg(lut[u - N]);
+            }
+        }
+        __syncthreads();
+
+        for (int i = 0; i < n; i++) {
+            const u32 at = rot[i];
+            if (at == 0) continue;   // X^0 - 1 = 0: nothing to add
+            u64 sum0[16], sum1[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) { sum0[q] = 0; sum1[q] = 0; }
+            const u64* g = a.bsk_hat + (size_t)i * (2 * l) * 2 * N;
+            for (int c = 0; c < 2; c++) {
+                const u64* A = acc + c * N;
+                for (int j = 1; j <= l; j++) {
+                    u64 x[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {   // digit j of (X^at - 1) * acc_c
+                        const int idx = q * T + tid;
+                        const u32 u = (idx + 2 * N - at) & (2 * N - 1);
+                        const u64 r = u < N ? A[u] : fneg(A[u - N]);
+                        x[q] = digit_of(round_top(fsub(r, A[idx]), tot), bl, l, j);
+                    }
+                    ntt_forward<L>(x, buf, a.tw, tid);
+                    const u64* row = g + (size_t)(c * l + (j - 1)) * 2 * N;
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        sum0[q] = fadd(sum0[q], fmul(x[q], __ldg(row + q * T + tid)));
+                        sum1[q] = fadd(sum1[q], fmul(x[q], __ldg(row + N + q * T + tid)));
+                    }
+                }
+            }
+            ntt_inverse<L>(sum0, buf, a.twi, tid);
+            ntt_inverse<L>(sum1, buf, a.twi, tid);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int idx = q * T + tid;
+                acc[idx] = fadd(acc[idx], sum0[q]);
+                acc[N + idx] = fadd(acc[N + idx], sum1[q]);
+            }
+            __syncthreads();
+        }
+
+        // sample extraction of the constant coefficient
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int t = q * T + tid;
+            out[t] = t == 0 ? acc[0] : fneg(acc[N - t]);
+        }
+        if (tid == 0) out[N] = acc[N];
+    }
+}
+
+// ----------------------------------------------------------------------------
+// keyswitch big (kN) -> small (n): out = (0, b) - sum_i sum_j digit_ij * ksk[i][j]
+// CTA = 128 output columns x JT ciphertexts; digits staged in shared memory per chunk.
+constexpr int KS_COLS = 128, KS_JT = 8, KS_CHUNK = 64;
+
+__global__ void __launch_bounds__(KS_COLS) keyswitch_kernel(const u64* __restrict__ in, const u64* __restrict__ ksk,
+                                                            u64* __restrict__ out, int M, int kN, int n, int bl, int l) {
+    extern __shared__ int dg[];   // [KS_CHUNK][l][KS_JT]
+    const int tid = threadIdx.x, t = blockIdx.x * KS_COLS + tid;
+    const int job0 = blockIdx.y * KS_JT;
+    const int njob = min(KS_JT, M - job0);
+    const int tot = bl * l;
+    const bool live = t <= n;
+    u64 lo[KS_JT], hi[KS_JT];
+#pragma unroll
+    for (int jb = 0; jb < KS_JT; jb++) { lo[jb] = 0; hi[jb] = 0; }
+
+    for (int i0 = 0; i0 < kN; i0 += KS_CHUNK) {
+        const int ci = min(KS_CHUNK, kN - i0);
+        __syncthreads();
+        for (int e = tid; e < KS_CHUNK * KS_JT; e += KS_COLS) {
+            const int jb = e / KS_CHUNK, ii = e % KS_CHUNK;
+            u64 r = 0;
+            if (jb < njob && ii < ci) r = round_top(in[(size_t)(job0 + jb) * (kN + 1) + i0 + ii], tot);
+            const u64 B = 1ULL << bl;
+            for (int lev = l; lev >= 1; lev--) {
+                u64 d = r & (B - 1);
+                r >>= bl;
+                int sd = (int)d;
+                if (d >= (B >> 1)) { r += 1; sd = (int)d - (int)B; }
+                dg[(ii * l + (lev - 1)) * KS_JT + jb] = sd;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            for (int ii = 0; ii < ci; ii++) {
+                for (int j = 0; j < l; j++) {
+                    const u64 kv = __ldg(ksk + ((size_t)(i0 + ii) * l + j) * (n + 1) + t);
+                    const u64 kneg = fneg(kv);
+                    const int* d = dg + (ii * l + j) * KS_JT;
+#pragma unroll
+                    for (int jb = 0; jb < KS_JT; jb++) {
+                        const int sd = d[jb];
+                        if (sd == 0) continue;
+                        const u64 m = sd > 0 ? (u64)sd : (u64)(-sd);
+                        const u64 v = sd > 0 ? kv : kneg;
+                        const u64 pl = m * v, ph = __umul64hi(m, v);
+                        lo[jb] += pl;
+                        hi[jb] += ph + (lo[jb] < pl);
+                    }
+                }
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int jb = 0; jb < KS_JT; jb++) {
+            if (jb >= njob) break;
+            const u64 base = t == n ? in[(size_t)(job0 + jb) * (kN + 1) + kN] : 0;
+            out[(size_t)(job0 + jb) * (n + 1) + t] = fsub(base, freduce128(lo[jb], hi[jb]));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
+// leveled linear combinations: out[j][b] = sum_t coef[t] * vals[idx[t]][b] + konst[j] (on the body)
+__global__ void __launch_bounds__(256) lincomb_kernel(const u64* __restrict__ vals, const int* __restrict__ row_ptr,
+                                                      const int* __restrict__ idx, const u64* __restrict__ coef,
+                                                      const u64* __restrict__ konst, u64* __restrict__ out,
+                                                      int W, int batch) {
+    const int f = blockIdx.x;
+    const int j = f / batch, b = f - j * batch;
+    const int t0 = row_ptr[j], t1 = row_ptr[j + 1];
+    u64* o = out + (size_t)f * W;
+    for (int w = blockIdx.y * blockDim.x + threadIdx.x; w < W; w += gridDim.y * blockDim.x) {
+        u64 s = w == W - 1 ? konst[j] : 0;
+        for (int t = t0; t < t1; t++) {
+            const u64 c = coef[t];
+            const u64 v = vals[((size_t)idx[t] * batch + b) * W + w];
+            if (c == 1) s = fadd(s, v);
+            else if (c == BMI_P - 1) s = fsub(s, v);
+            else s = fadd(s, fmul(c, v));
+        }
+        o[w] = s;
+    }
+}
