@@ -1,0 +1,132 @@
+"""GPU execution of a levelled Program through the C ABI (one launch group per level).
+
+PyTorch only owns device memory and streams here; every arithmetic step is a kernel of
+libbmi_tfhe.so (bmi_lincomb -> bmi_keyswitch -> bmi_pbs).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import params as PR
+from ..native import Engine
+from .program import Program
+
+P = PR.P
+
+
+def _field(vals, scale=1):
+    """signed python/numpy ints -> uint64 field elements (times scale), returned as an int64-typed view"""
+    out = np.array([(int(v) * scale) % P for v in vals], dtype=np.uint64)
+    return out.view(np.int64)
+
+
+class Executor:
+    def __init__(self, program: Program, params: PR.TfheParams, engine: Engine, device: int = 0,
+                 rank: int = 0, world: int = 1, group=None):
+        self.prog, self.params, self.eng = program, params, engine
+        self.dev = torch.device("cuda", device)
+        self.rank, self.world, self.group = rank, world, group
+        W1 = params.big_dim + 1
+        self.W1 = W1
+        engine.load_luts(program.lut_polynomials(params.N))
+        scale = PR.delta(program.width)
+        lv = program.levels
+
+        def cat(arrs, dtype):
+            return np.concatenate([np.asarray(a, dtype) for a in arrs]) if arrs else np.zeros(0, dtype)
+
+        # per-level arrays concatenated once; each level addresses its slice
+        self.ks_off = np.cumsum([0] + [len(l.konst) for l in lv])
+        self.nz_off = np.cumsum([0] + [len(l.idx) for l in lv])
+        self.pbs_off = np.cumsum([0] + [len(l.job_ks) for l in lv])
+        row_ptr = cat([l.row_ptr.astype(np.int64) for l in lv], np.int64)      # each level keeps its own n_ks+1 entries
+        self.rp_off = np.cumsum([0] + [len(l.row_ptr) for l in lv])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+        self.d_row_ptr = t(row_ptr.astype(np.int32))
+        self.d_idx = t(cat([l.idx for l in lv], np.int32))
+        self.d_coef = t(_field(cat([l.coef for l in lv], np.int64)))
+        self.d_konst = t(_field(cat([l.konst for l in lv], np.int64), scale))
+        self.d_job_ks = t(cat([l.job_ks for l in lv], np.int32))
+        self.d_job_lut = t(cat([l.job_lut for l in lv], np.int32))
+        self.d_job_out = t(cat([l.job_out for l in lv], np.int32))
+        self.d_out_ptr = t(program.out_row_ptr.astype(np.int32))
+        self.d_out_idx = t(program.out_idx.astype(np.int32))
+        self.d_out_coef = t(_field(program.out_coef))
+        self.d_out_konst = t(_field(program.out_konst, scale))
+        self.max_ks = max((len(l.konst) for l in lv), default=1)
+        self.max_pbs = max((len(l.job_ks) for l in lv), default=1)
+        self._batch = 0
+
+    def _ensure(self, batch):
+        if batch == self._batch:
+            return
+        p = self.params
+        self.vals = torch.zeros((self.prog.n_slots, batch, self.W1), dtype=torch.int64, device=self.dev)
+        self.ks_in = torch.empty((self.max_ks * batch, self.W1), dtype=torch.int64, device=self.dev)
+        self.small = torch.empty((self.max_ks * batch, p.n + 1), dtype=torch.int64, device=self.dev)
+        n_out = len(self.prog.out_konst)
+        self.outs = torch.empty((n_out, batch, self.W1), dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            self.stage = torch.empty((self.max_pbs, batch, self.W1), dtype=torch.int64, device=self.dev)
+        self._batch = batch
+
+    def run(self, input_cts: np.ndarray) -> np.ndarray:
+        """input_cts: [n_inputs][kN+1] or [batch][n_inputs][kN+1] uint64 (host) -> output ciphertexts (host)"""
+        x = np.ascontiguousarray(input_cts, dtype=np.uint64)
+        single = x.ndim == 2
+        if single:
+            x = x[None]
+        batch = x.shape[0]
+        self._ensure(batch)
+        host = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2)).view(np.int64))
+        self.vals[: self.prog.n_inputs].copy_(host, non_blocking=True)
+        self.run_device(batch)
+        out = self.outs.cpu().numpy().view(np.uint64).transpose(1, 0, 2)
+        return out[0] if single else np.ascontiguousarray(out)
+
+    def run_device(self, batch):
+        """inputs already in self.vals[:n_inputs]; leaves output ciphertexts in self.outs"""
+        eng, prog = self.eng, self.prog
+        for li in range(len(prog.levels)):
+            self._level(li, batch)
+        eng.lincomb(self.vals, self.d_out_ptr, self.d_out_idx, self.d_out_coef, self.d_out_konst, self.outs,
+                    len(prog.out_konst), batch)
+
+    def _level(self, li, batch):
+        eng = self.eng
+        k0, k1 = self.ks_off[li], self.ks_off[li + 1]
+        p0, p1 = self.pbs_off[li], self.pbs_off[li + 1]
+        n_ks, n_pbs = int(k1 - k0), int(p1 - p0)
+        if n_pbs == 0:
+            return
+        # this level's CSR rows index the concatenated idx/coef arrays through their own row_ptr (level-local offsets)
+        rp = self.d_row_ptr[self.rp_off[li]: self.rp_off[li + 1]]
+        idx = self.d_idx[self.nz_off[li]: self.nz_off[li + 1]]
+        coef = self.d_coef[self.nz_off[li]: self.nz_off[li + 1]]
+        konst = self.d_konst[k0:k1]
+        job_ks, job_lut, job_out = self.d_job_ks[p0:p1], self.d_job_lut[p0:p1], self.d_job_out[p0:p1]
+        if self.world == 1:
+            eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch)
+            eng.keyswitch(self.ks_in, self.small, n_ks * batch)
+            eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch)
+            return
+        self._level_sharded(li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs)
+
+    # ---- one box, several GPUs: each rank bootstraps a contiguous share of the level's lookups, then the
+    # output ciphertexts are all-gathered over NVLink (keys are replicated on every GPU)
+    def _level_sharded(self, li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs):
+        import torch.distributed as dist
+        eng = self.eng
+        per = (n_pbs + self.world - 1) // self.world
+        lo, hi = min(self.rank * per, n_pbs), min((self.rank + 1) * per, n_pbs)
+        # every rank forms all keyswitch inputs it needs; for simplicity all rows (cheap next to the bootstraps)
+        eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch)
+        eng.keyswitch(self.ks_in, self.small, n_ks * batch)
+        stage = self.stage[: per * self.world]
+        if hi > lo:
+            local_out = torch.arange(lo, hi, dtype=torch.int32, device=self.dev)
+            eng.pbs(self.small, job_ks[lo:hi], job_lut[lo:hi], local_out, stage, hi - lo, batch)
+        mine = stage[self.rank * per: (self.rank + 1) * per]
+        dist.all_gather_into_tensor(stage, mine.clone(), group=self.group)
+        self.vals.index_copy_(0, job_out.long(), stage[:n_pbs])

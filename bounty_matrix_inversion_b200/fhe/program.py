@@ -1,0 +1,296 @@
+"""Lowering of a trace into a levelled TFHE program, and its clear-text evaluator.
+
+A Program is what the engine executes (one batched launch group per level):
+
+  level L:  lincomb rows (CSR over value slots)  ->  keyswitch  ->  PBS jobs (ks row, LUT, out slot)
+  outputs:  lincomb rows over value slots
+
+All ciphertexts of a program share one message width W (plaintext scale 2^(63-W)); a lookup
+whose input ranges over [lo, hi] on the inputset reads the table at (value + offset) with the
+range centred in [0, 2^W).  W is the smallest width that fits every lookup input range, the
+quantity Concrete's bit-width assignment derives from the same inputset
+(/root/reference/matrix_inversion/qfloat_matrix_inversion.py:981-1004).
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .. import params as PR
+
+
+@dataclass
+class Level:
+    row_ptr: np.ndarray      # [n_ks + 1] int32
+    idx: np.ndarray          # [nnz] int32 value slots
+    coef: np.ndarray         # [nnz] int64 signed coefficients
+    konst: np.ndarray        # [n_ks] int64 signed constants (message units, offset included)
+    job_ks: np.ndarray       # [n_pbs] int32 row of this level's keyswitch batch
+    job_lut: np.ndarray      # [n_pbs] int32
+    job_out: np.ndarray      # [n_pbs] int32 value slot
+
+
+@dataclass
+class Program:
+    width: int
+    n_inputs: int
+    n_slots: int
+    input_slots: np.ndarray
+    levels: list
+    out_row_ptr: np.ndarray
+    out_idx: np.ndarray
+    out_coef: np.ndarray
+    out_konst: np.ndarray
+    out_shape: tuple
+    tables: np.ndarray       # [n_luts][2^W] int64 table outputs (message units)
+    nu2: int                 # largest squared 2-norm of a lookup input's linear combination
+    stats: dict = field(default_factory=dict)
+
+    @property
+    def n_pbs(self):
+        return int(sum(len(l.job_ks) for l in self.levels))
+
+    @property
+    def n_ks(self):
+        return int(sum(len(l.konst) for l in self.levels))
+
+    def lut_polynomials(self, N: int) -> np.ndarray:
+        W = self.width
+        return np.stack([PR.lut_polynomial([PR.encode(int(t), W) for t in tab], W, N) for tab in self.tables])
+
+    # ------------------------------------------------------------ (de)serialisation
+    def save(self, path, **extra):
+        """compiled programs travel as .npz (the compile step needs the circuit's Python source; running does not)"""
+        lv = self.levels
+        cat = lambda xs, dt: np.concatenate([np.asarray(x, dt) for x in xs]) if xs else np.zeros(0, dt)
+        np.savez_compressed(
+            path, width=self.width, n_inputs=self.n_inputs, n_slots=self.n_slots, input_slots=self.input_slots,
+            ks_counts=np.array([len(l.konst) for l in lv], np.int64), nz_counts=np.array([len(l.idx) for l in lv], np.int64),
+            pbs_counts=np.array([len(l.job_ks) for l in lv], np.int64),
+            row_ptr=cat([l.row_ptr for l in lv], np.int32), idx=cat([l.idx for l in lv], np.int32),
+            coef=cat([l.coef for l in lv], np.int32), konst=cat([l.konst for l in lv], np.int32),
+            job_ks=cat([l.job_ks for l in lv], np.int32), job_lut=cat([l.job_lut for l in lv], np.int16),
+            job_out=cat([l.job_out for l in lv], np.int32), out_row_ptr=self.out_row_ptr, out_idx=self.out_idx,
+            out_coef=self.out_coef, out_konst=self.out_konst, out_shape=np.array(self.out_shape, np.int64),
+            tables=self.tables.astype(np.int16 if self.width < 15 else np.int64), nu2=self.nu2,
+            stats=np.array(repr(self.stats)), **extra)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path, allow_pickle=False)
+        ks, nz, pb = z["ks_counts"], z["nz_counts"], z["pbs_counts"]
+        ko, no, po = np.cumsum(np.r_[0, ks]), np.cumsum(np.r_[0, nz]), np.cumsum(np.r_[0, pb])
+        ro = np.cumsum(np.r_[0, ks + 1])
+        levels = []
+        for i in range(len(ks)):
+            levels.append(Level(z["row_ptr"][ro[i]:ro[i + 1]].astype(np.int32), z["idx"][no[i]:no[i + 1]].astype(np.int32),
+                                z["coef"][no[i]:no[i + 1]].astype(np.int64), z["konst"][ko[i]:ko[i + 1]].astype(np.int64),
+                                z["job_ks"][po[i]:po[i + 1]].astype(np.int32), z["job_lut"][po[i]:po[i + 1]].astype(np.int32),
+                                z["job_out"][po[i]:po[i + 1]].astype(np.int32)))
+        import ast
+        prog = cls(int(z["width"]), int(z["n_inputs"]), int(z["n_slots"]), z["input_slots"].astype(np.int32), levels,
+                   z["out_row_ptr"].astype(np.int32), z["out_idx"].astype(np.int32), z["out_coef"].astype(np.int64),
+                   z["out_konst"].astype(np.int64), tuple(int(v) for v in z["out_shape"]), z["tables"].astype(np.int64),
+                   int(z["nu2"]))
+        prog.stats = ast.literal_eval(str(z["stats"]))
+        return prog
+
+    # ------------------------------------------------------------ clear evaluation
+    def evaluate_clear(self, inputs: np.ndarray) -> np.ndarray:
+        """run the levelled program on clear integers (what the ciphertexts hold); inputs [n_inputs] or
+        [batch][n_inputs] -> outputs shaped out_shape (with a leading batch axis if given)"""
+        x = np.asarray(inputs, dtype=np.int64)
+        single = x.ndim == 1
+        x = np.atleast_2d(x)
+        B, W = x.shape[0], self.width
+        vals = np.zeros((self.n_slots, B), np.int64)
+        vals[self.input_slots] = x.T
+        for lv in self.levels:
+            ks = _csr_apply(lv.row_ptr, lv.idx, lv.coef, lv.konst, vals)
+            if ks.size and (ks.min() < 0 or ks.max() >= (1 << W)):
+                raise OverflowError(f"lookup input outside the {W}-bit message space: [{ks.min()}, {ks.max()}]")
+            vals[lv.job_out] = self.tables[lv.job_lut[:, None], ks[lv.job_ks]]
+        out = _csr_apply(self.out_row_ptr, self.out_idx, self.out_coef, self.out_konst, vals)
+        out = out.T.reshape((B,) + tuple(self.out_shape))
+        return out[0] if single else out
+
+
+def _csr_apply(row_ptr, idx, coef, konst, vals):
+    n = len(konst)
+    out = np.repeat(konst[:, None], vals.shape[1], axis=1).astype(np.int64)
+    if len(idx):
+        rows = np.repeat(np.arange(n), np.diff(row_ptr))
+        np.add.at(out, rows, coef[:, None] * vals[idx])
+    return out
+
+
+# ------------------------------------------------------------------ lowering
+def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1) -> Program:
+    """trace: fhe.tracing.Trace after the circuit function ran; outputs: flat list of scalars
+    (ints / Aff) the function returned"""
+    n_in = trace.n_inputs
+    jobs = trace.jobs
+
+    # --- dead code elimination: only lookups the outputs depend on
+    live = np.zeros(len(jobs), bool)
+    stack = []
+    for o in outputs:
+        if not isinstance(o, int):
+            stack.extend(b for b in o.terms if b >= n_in)
+    while stack:
+        b = stack.pop()
+        j = b - n_in
+        if live[j]:
+            continue
+        live[j] = True
+        stack.extend(t for t in jobs[j].terms if t >= n_in)
+
+    # --- message width: every live lookup's input range must fit
+    W = min_width
+    for j in np.flatnonzero(live):
+        g = jobs[j].group
+        W = max(W, int(g.hi - g.lo).bit_length())
+    for o in outputs:
+        if not isinstance(o, int):
+            W = max(W, int(max(abs(int(o.vals.min())), abs(int(o.vals.max())))).bit_length())
+    W += slack_bits
+    size = 1 << W
+    dom = np.arange(size, dtype=np.int64)
+
+    # --- tables, common-subexpression elimination of lookups and of keyswitches
+    table_ids, tables = {}, []
+    lookup_ids = {}            # (src key, table id) -> representative base
+    alias = {}                 # base -> representative base
+    job_info = {}              # representative base -> (src key, offset, table id)
+    nu2 = 1
+
+    def resolve(b):
+        return alias.get(b, b)
+
+    for j in np.flatnonzero(live):        # jobs are in creation (topological) order
+        jb = jobs[j]
+        g = jb.group
+        offset = (size - (g.hi - g.lo + 1)) // 2 - g.lo           # centre [lo, hi] in [0, 2^W)
+        terms = {}
+        for b, c in jb.terms.items():
+            rb = resolve(b)
+            v = terms.get(rb, 0) + c
+            if v:
+                terms[rb] = v
+            else:
+                terms.pop(rb, None)
+        key = (tuple(sorted(terms.items())), jb.const + offset)
+        tab = np.asarray(jb.fn(dom - offset), dtype=np.int64)
+        if tab.shape != (size,):
+            tab = np.broadcast_to(tab, (size,)).copy()
+        # entries for inputs never seen on the inputset may be anything; arithmetic is mod 2^(W+1) anyway
+        tab = ((tab + size) % (2 * size)) - size
+        h = hashlib.blake2b(tab.tobytes(), digest_size=16).digest()
+        tid = table_ids.get(h)
+        if tid is None:
+            tid = table_ids[h] = len(tables)
+            tables.append(tab)
+        rep = lookup_ids.get((key, tid))
+        if rep is not None:
+            alias[jb.base] = rep
+            continue
+        lookup_ids[(key, tid)] = jb.base
+        job_info[jb.base] = (key, tid)
+        nu2 = max(nu2, sum(c * c for c in terms.values()))
+
+    # --- levels (as soon as possible)
+    level_of = {}
+    for base, (key, _tid) in job_info.items():
+        lv = 1
+        for b, _c in key[0]:
+            if b >= n_in:
+                lv = max(lv, level_of[b] + 1)
+        level_of[base] = lv
+    n_levels = max(level_of.values(), default=0)
+    by_level = [[] for _ in range(n_levels)]
+    for base, lv in level_of.items():
+        by_level[lv - 1].append(base)
+
+    # --- outputs as linear combinations of representatives
+    out_rows = []
+    for o in outputs:
+        if isinstance(o, int):
+            out_rows.append(({}, o))
+            continue
+        terms = {}
+        for b, c in o.terms.items():
+            rb = resolve(b)
+            v = terms.get(rb, 0) + c
+            if v:
+                terms[rb] = v
+            else:
+                terms.pop(rb, None)
+        out_rows.append((terms, o.const))
+
+    # --- liveness -> slot reuse
+    last_use = {b: 0 for b in range(n_in)}
+    for base, (key, _tid) in job_info.items():
+        for b, _c in key[0]:
+            last_use[b] = max(last_use.get(b, 0), level_of[base])
+    for terms, _k in out_rows:
+        for b in terms:
+            last_use[b] = n_levels + 1
+    slot_of, free, n_slots = {}, [], 0
+    for b in range(n_in):
+        slot_of[b] = n_slots
+        n_slots += 1
+    expiring = [[] for _ in range(n_levels + 2)]
+    for b in range(n_in):
+        expiring[last_use[b]].append(b)
+    levels = []
+    for li, bases in enumerate(by_level, start=1):
+        for b in bases:
+            if free:
+                slot_of[b] = free.pop()
+            else:
+                slot_of[b] = n_slots
+                n_slots += 1
+            expiring[max(last_use.get(b, li), li)].append(b)
+        # keyswitch rows shared by lookups with the same input
+        ks_rows, ks_index = [], {}
+        job_ks, job_lut, job_out = [], [], []
+        for b in bases:
+            key, tid = job_info[b]
+            r = ks_index.get(key)
+            if r is None:
+                r = ks_index[key] = len(ks_rows)
+                ks_rows.append(key)
+            job_ks.append(r)
+            job_lut.append(tid)
+            job_out.append(slot_of[b])
+        row_ptr = np.zeros(len(ks_rows) + 1, np.int32)
+        idx, coef, konst = [], [], []
+        for r, (terms, k) in enumerate(ks_rows):
+            for b, c in terms:
+                idx.append(slot_of[b])
+                coef.append(c)
+            row_ptr[r + 1] = len(idx)
+            konst.append(k)
+        levels.append(Level(row_ptr, np.asarray(idx, np.int32), np.asarray(coef, np.int64), np.asarray(konst, np.int64),
+                            np.asarray(job_ks, np.int32), np.asarray(job_lut, np.int32), np.asarray(job_out, np.int32)))
+        for b in expiring[li]:              # values last read at this level free their slot for the next one
+            free.append(slot_of[b])
+
+    out_ptr = np.zeros(len(out_rows) + 1, np.int32)
+    oidx, ocoef, okonst = [], [], []
+    for r, (terms, k) in enumerate(out_rows):
+        for b, c in sorted(terms.items()):
+            oidx.append(slot_of[b])
+            ocoef.append(c)
+        out_ptr[r + 1] = len(oidx)
+        okonst.append(k)
+
+    prog = Program(W, n_in, n_slots, np.arange(n_in, dtype=np.int32), levels, out_ptr, np.asarray(oidx, np.int32),
+                   np.asarray(ocoef, np.int64), np.asarray(okonst, np.int64), tuple(out_shape),
+                   np.stack(tables) if tables else np.zeros((1, size), np.int64), int(nu2))
+    prog.stats = {"traced_lookups": len(jobs), "live_lookups": int(live.sum()), "pbs": prog.n_pbs, "keyswitches": prog.n_ks,
+                  "levels": n_levels, "tables": len(tables), "slots": n_slots, "width": W, "nu2": int(nu2),
+                  "max_level_pbs": max((len(l.job_ks) for l in levels), default=0)}
+    return prog

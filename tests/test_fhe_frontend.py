@@ -1,0 +1,146 @@
+"""CPU tests of the tracing front-end and the lowering (no GPU, no encryption): the compiled program's
+clear evaluation must equal plain numpy on the same function, and the lookup counts must show fusing."""
+import numpy as np
+import pytest
+
+from bounty_matrix_inversion_b200 import fhe, params as PR
+
+rng = np.random.default_rng(7)
+
+
+def compile_(fn, inputset, names=("x", "y")):
+    return fhe.Compiler(fn, {n: "encrypted" for n in names}).compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
+
+
+def pairs(lo, hi, shape, count=60):
+    return [(rng.integers(lo, hi, shape), rng.integers(lo, hi, shape)) for _ in range(count)]
+
+
+def check(fn, inputset, names=("x", "y")):
+    c = compile_(fn, inputset, names)
+    for args in inputset[:25]:
+        want = np.asarray(fn(*args))
+        assert np.array_equal(c.simulate(*args), want), (args, c.simulate(*args), want)
+    return c
+
+
+def test_outside_tracing_zeros_are_numpy():
+    z, o = fhe.zeros((2, 3)), fhe.ones(4)
+    assert isinstance(z, np.ndarray) and z.dtype == np.int64 and not z.any() and o.sum() == 4
+
+
+def test_leveled_ops_cost_no_lookup():
+    c = check(lambda x, y: 3 * x - y + 2 + np.sum(x) - (-y), pairs(-4, 5, (3,)))
+    assert c.statistics["pbs"] == 0 and c.statistics["levels"] == 0
+
+
+def test_univariate_chain_fuses_into_one_lookup():
+    c = check(lambda x, y: (np.abs(x - y) // 2) * 3 + 1, pairs(0, 8, (4,)))
+    assert c.statistics["pbs"] == 4                     # one per element, not three
+
+
+def test_comparison_family():
+    def fn(x, y):
+        out = fhe.zeros((8, 3))
+        out[0] = x < y; out[1] = x <= y; out[2] = x > y; out[3] = x >= y
+        out[4] = x == y; out[5] = x != y; out[6] = x < 2; out[7] = 1 - (x >= 1)
+        return out
+    c = check(fn, pairs(-3, 4, (3,)))
+    assert c.statistics["keyswitches"] <= 3 * 2          # x-y shared by six tables, x by two
+
+
+def test_encrypted_product_is_two_lookups_each():
+    c = check(lambda x, y: x * y, pairs(-3, 4, (5,)))
+    assert c.statistics["pbs"] == 10
+
+
+def test_floor_div_mod_sign_abs():
+    check(lambda x, y: (x + y) // 3 + (x + y) % 3 * 10 + np.sign(x - y) * 100 + abs(x), pairs(-5, 6, (2, 2)))
+
+
+def test_bitwise_between_encrypted_bits():
+    def fn(x, y):
+        a, b = x > 0, y > 0
+        return (a & b) + 2 * (a | b) + 4 * (a ^ b) + 8 * (a & 1)
+    check(fn, pairs(-2, 3, (4,)))
+
+
+def test_indexing_assignment_concatenate_reshape():
+    def fn(x, y):
+        z = np.concatenate((x[1:], y[:2], fhe.zeros(1)), axis=0)
+        m = fhe.zeros((2, 3))
+        m[0, :] = z[:3]
+        m[1, 1:] = (z[3:5] * 2).reshape(2)
+        m[:, 0] = m[:, 0] + 1
+        t = m.flatten()
+        t[-1] += x[0]
+        return np.reshape(t, (3, 2))
+    check(fn, pairs(0, 5, (3,)))
+
+
+def test_carry_propagation_like_base_p_addition():
+    """the reference's base_p_addition loop (base_p_arrays.py:100-103) written against this front-end"""
+    def fn(x, y):
+        out, carry = fhe.zeros(x.size), 0
+        for i in range(x.size):
+            s = x[-i - 1] + y[-i - 1] + carry
+            out[-i - 1] = s % 2
+            carry = s // 2
+        return out
+    c = check(fn, pairs(0, 2, (6,)))
+    assert c.statistics["levels"] == 6 and c.statistics["pbs"] == 11      # last carry is dead code
+
+
+def test_common_lookups_are_shared_and_dead_ones_dropped():
+    def fn(x, y):
+        a = (x + y) // 2
+        b = (x + y) // 2          # same table on the same input
+        _dead = (x - y) % 3
+        return a + b
+    c = check(fn, pairs(0, 6, (2,)))
+    assert c.statistics["traced_lookups"] == 4 and c.statistics["pbs"] == 2
+
+
+def test_fhe_univariate_and_where():
+    f = fhe.univariate(lambda v: np.where(v & 1 == 0, 0, v >> 1))
+    check(lambda x, y: f(x * 2 + (y > 2)), pairs(0, 6, (3,)))
+
+
+def test_constant_folding_of_zero_arrays():
+    c = check(lambda x, y: fhe.zeros(3) * x + fhe.ones(3) * y, pairs(0, 4, (3,)))
+    assert c.statistics["pbs"] == 0
+
+
+def test_errors():
+    c = fhe.Compiler(lambda x: x, {"x": "encrypted"})
+    with pytest.raises(ValueError):
+        c.compile([])
+    with pytest.raises(NotImplementedError):
+        fhe.Compiler(lambda x: x, {"x": "clear"})
+    with pytest.raises(TypeError):
+        compile_(lambda x, y: x if x[0] else y, pairs(0, 2, (2,)))
+    with pytest.raises(TypeError):
+        compile_(lambda x, y: x / y, pairs(1, 3, (2,)))
+    circ = compile_(lambda x, y: x + y, pairs(0, 2, (2,)))
+    with pytest.raises(ValueError):
+        circ.simulate(np.zeros(3), np.zeros(2))
+
+
+def test_width_and_norm_drive_parameter_choice():
+    extremes = [(np.zeros(8, np.int64), np.zeros(8, np.int64)), (np.ones(8, np.int64), np.ones(8, np.int64))]
+    c = compile_(lambda x, y: (np.sum(x) + np.sum(y)) // 4, pairs(0, 2, (8,)) + extremes)
+    assert c.program.width == 5 and c.program.nu2 == 16            # values 0..16 need 17 table entries
+    p = PR.optimize(3, 4)
+    assert p.k == 1 and PR.failure_sigmas(p, 3, 4) >= 6.5 and p.N >= 1024
+    assert PR.failure_sigmas(p, 4, 4) < 6.5 or PR.cost(PR.optimize(4, 4)) >= PR.cost(p)
+
+
+def test_program_roundtrip(tmp_path):
+    c = compile_(lambda x, y: (x * y + 3) // 2, pairs(0, 4, (3,)))
+    path = str(tmp_path / "p.npz")
+    c.program.save(path)
+    from bounty_matrix_inversion_b200.fhe.program import Program
+    q = Program.load(path)
+    x = rng.integers(0, 4, (5, 6))
+    assert np.array_equal(q.evaluate_clear(x), c.program.evaluate_clear(x))
+    assert q.stats == c.program.stats

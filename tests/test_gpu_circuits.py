@@ -1,0 +1,67 @@
+"""GPU: the reference's circuits (compiled programs in tests/golden/) executed under encryption through the
+C ABI; decrypted digits must equal the reference's clear QFloat path, and the ciphertexts must equal the
+CPU oracle's execution of the same program bit for bit."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from bounty_matrix_inversion_b200 import fhe, params as PR
+from bounty_matrix_inversion_b200.fhe.program import Program
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+TOY_FOR_WIDTH = {3: PR.TOY_1024, 4: PR.TOY_2048, 5: PR.TOY_4096, 6: PR.TOY_8192}
+
+
+def load(name):
+    path = os.path.join(HERE, "golden", name + ".npz")
+    z = np.load(path)
+    return Program.load(path), z["golden_inputs"].astype(np.int64), z["golden_outputs"].astype(np.int64)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_encrypted_run_matches_reference_digits(path, native):
+    name = os.path.basename(path)[:-4]
+    prog, x, want = load(name)
+    circuit = fhe.Circuit.from_program(prog, TOY_FOR_WIDTH[prog.width])
+    enc = circuit.encrypt_batch([(row,) for row in x])            # every golden input is one batch lane
+    got = circuit.decrypt(circuit.run(enc))
+    assert np.array_equal(np.stack(got), want)
+
+
+def test_ciphertexts_equal_oracle_execution(native, oracle):
+    from oracle_exec import run_program_oracle
+    prog, x, want = load("qf_add_medium")
+    prm = PR.TOY_1024
+    circuit = fhe.Circuit.from_program(prog, prm)
+    enc = circuit.encrypt(x[0])
+    out = circuit.run(enc)
+    ref = run_program_oracle(oracle, prog, prm, circuit.keys.bsk, circuit.keys.ksk, enc.cts)
+    assert np.array_equal(out.cts, ref)
+    assert np.array_equal(circuit.decrypt(out), want[0])
+
+
+def test_secure_parameters_qfloat_add(native):
+    """128-bit parameter set chosen by the noise model for this circuit's width and norm"""
+    prog, x, want = load("qf_add_medium")
+    circuit = fhe.Circuit.from_program(prog)
+    assert circuit.params.N >= 1024 and PR.failure_sigmas(circuit.params, prog.width, prog.nu2) >= 6.5
+    got = circuit.decrypt(circuit.run(circuit.encrypt_batch([(row,) for row in x[:4]])))
+    assert np.array_equal(np.stack(got), want[:4])
+
+
+def test_compile_and_run_small_function(native):
+    """fhe.Compiler -> encrypt -> run -> decrypt on a function written against the front-end"""
+    rng = np.random.default_rng(1)
+
+    def fn(x, y):
+        s = x + y
+        return np.concatenate(((s // 2) * (x > y), (s % 2).reshape(-1)), axis=0)
+
+    inputset = [(rng.integers(0, 4, 3), rng.integers(0, 4, 3)) for _ in range(40)]
+    circuit = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
+    for x, y in inputset[:5]:
+        assert np.array_equal(circuit.encrypt_run_decrypt(x, y), fn(x, y))
