@@ -57,6 +57,20 @@ class Executor:
         self.max_ks = max((len(l.konst) for l in lv), default=1)
         self.max_pbs = max((len(l.job_ks) for l in lv), default=1)
         self._batch = 0
+        self.profile = None          # list of (start event, end event, jobs) around every PBS launch when profiling
+
+    def collect_profile(self):
+        """PBS-kernel time measured with CUDA events on the launching stream, and the algorithmic work it covers"""
+        torch.cuda.synchronize(self.dev)
+        p = self.params
+        prof = self.profile or []
+        ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+        jobs = sum(j for _, _, j in prof)
+        per_pbs_bytes = p.bsk_bytes() + (p.n + 1) * 8 + p.N * 8 + (p.big_dim + 1) * 8
+        butterflies = (p.k + 1) * (p.bsk_l + 1) * (p.N // 2) * p.logN
+        per_pbs_int = p.n * (butterflies * 26 + (p.k + 1) ** 2 * p.bsk_l * p.N * 22 + (p.k + 1) * p.bsk_l * p.N * 12)
+        return {"pbs_ms": ms, "pbs_launches": len(prof), "pbs_jobs": jobs, "alg_bytes": jobs * per_pbs_bytes,
+                "int_ops": jobs * per_pbs_int}
 
     def _ensure(self, batch):
         if batch == self._batch:
@@ -109,7 +123,14 @@ class Executor:
         if self.world == 1:
             eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch)
             eng.keyswitch(self.ks_in, self.small, n_ks * batch)
-            eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch)
+            if self.profile is not None:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch)
+                b.record()
+                self.profile.append((a, b, n_pbs * batch))
+            else:
+                eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch)
             return
         self._level_sharded(li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs)
 
