@@ -33,10 +33,13 @@ struct bmi_ctx {
     int n_luts = 0;
     int num_sms = 148;
     int64_t launches = 0;
+    int pbs_mode = 0;   // 0 auto (cluster kernel, build chosen per launch), 1 cluster kernel latency build, 2 single-CTA kernel
     // scratch for the host-buffer convenience path
     u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
     int *w_idx = nullptr, *w_lut = nullptr;
     int64_t w_cap = 0;
+    u64* ks_partial = nullptr;   // per-slice keyswitch sums (small batches)
+    size_t ks_partial_cap = 0;
 };
 
 namespace {
@@ -46,6 +49,9 @@ size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c-
 template <int L>
 int setup_attrs(const bmi_ctx* c) {
     CK(cudaFuncSetAttribute(pbs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, throughput_ctas_per_sm<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)pbs_smem(c)));
     CK(cudaFuncSetAttribute(bsk_convert_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(polymul_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     return BMI_OK;
@@ -63,7 +69,19 @@ template <int L>
 int launch_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) {
     const int64_t total = (int64_t)a.njobs * a.batch;
     const unsigned grid = (unsigned)std::min<int64_t>(total, 1 << 20);
-    pbs_kernel<L><<<grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);
+    if (c->pbs_mode == 2) {
+        pbs_kernel<L><<<grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);                   // one CTA per ciphertext
+    } else {
+        // CTA pair per ciphertext.  While the launch fits the resident CTA pairs of the all-in-registers build,
+        // latency wins; beyond one wave the higher-occupancy build does.
+        int resident = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, 1>, NttCfg<L>::T, pbs_smem(c));
+        const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
+        if (c->pbs_mode == 1 || total <= one_wave)
+            pbs_cluster_kernel<L, 1><<<2 * grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);
+        else
+            pbs_cluster_kernel<L, throughput_ctas_per_sm<L>()><<<2 * grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);
+    }
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
@@ -150,6 +168,7 @@ int bmi_ctx_destroy(bmi_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk); cudaFree(c->d_ksk); cudaFree(c->d_luts);
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
+    cudaFree(c->ks_partial);
     delete c;
     return BMI_OK;
 }
@@ -197,6 +216,12 @@ int bmi_ctx_load_luts(bmi_ctx* c, const uint64_t* h_luts, int32_t n_luts) {
 
 int64_t bmi_ctx_launch_count(const bmi_ctx* c) { return c ? c->launches : 0; }
 
+int bmi_ctx_set_pbs_mode(bmi_ctx* c, int32_t mode) {
+    if (!c || mode < 0 || mode > 2) { set_error("invalid argument"); return BMI_EINVAL; }
+    c->pbs_mode = mode;
+    return BMI_OK;
+}
+
 int bmi_lincomb(bmi_ctx* c, const uint64_t* d_vals, const int32_t* d_row_ptr, const int32_t* d_idx, const uint64_t* d_coef,
                 const uint64_t* d_konst, uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
     if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
@@ -213,12 +238,34 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
     if (!c || count < 0) { set_error("invalid argument"); return BMI_EINVAL; }
     if (!c->d_ksk) { set_error("keyswitch key not loaded"); return BMI_ESTATE; }
     if (count == 0) return BMI_OK;
-    dim3 grid((c->p.n + 1 + KS_COLS - 1) / KS_COLS, (unsigned)((count + KS_JT - 1) / KS_JT));
+    const int cols = (c->p.n + 1 + KS_COLS - 1) / KS_COLS, tiles = (int)((count + KS_JT - 1) / KS_JT);
+    const int kN = c->p.k * c->p.N;
+    // enough CTAs for ~3 per SM: small batches split the input coefficients over blockIdx.z
+    int slices = std::max(1, std::min(kN / KS_CHUNK, (3 * c->num_sms) / std::max(1, cols * tiles)));
+    int slice = ((kN + slices - 1) / slices + KS_CHUNK - 1) / KS_CHUNK * KS_CHUNK;
+    slices = (kN + slice - 1) / slice;
+    if (slices > 1) {
+        const size_t need = (size_t)slices * count * (c->p.n + 1);
+        if (need > c->ks_partial_cap) {
+            cudaFree(c->ks_partial);
+            c->ks_partial = nullptr; c->ks_partial_cap = 0;
+            CK(cudaMalloc(&c->ks_partial, need * 8));
+            c->ks_partial_cap = need;
+        }
+    }
+    dim3 grid(cols, tiles, slices);
     const size_t smem = (size_t)KS_CHUNK * c->p.ksk_l * KS_JT * sizeof(int);
-    keyswitch_kernel<<<grid, KS_COLS, smem, (cudaStream_t)stream>>>(d_in, c->d_ksk, d_out, (int)count, c->p.k * c->p.N, c->p.n,
-                                                                   c->p.ksk_bl, c->p.ksk_l);
+    keyswitch_kernel<<<grid, KS_COLS, smem, (cudaStream_t)stream>>>(d_in, c->d_ksk, d_out, c->ks_partial, (int)count, kN, c->p.n,
+                                                                   c->p.ksk_bl, c->p.ksk_l, slice);
     c->launches++;
     CK(cudaGetLastError());
+    if (slices > 1) {
+        const size_t elems = (size_t)count * (c->p.n + 1);
+        keyswitch_finish_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, c->ks_partial, d_out, (int)count,
+                                                                                                  kN, c->p.n, slices);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     return BMI_OK;
 }
 

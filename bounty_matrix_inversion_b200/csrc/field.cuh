@@ -49,6 +49,55 @@ BMI_HD u64 fmul(u64 a, u64 b) {
 #endif
 }
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// Device fast path.  "lazy" values are any u64 congruent to the field element (possibly >= p).
+// Carry chains are written in PTX so that ptxas keeps them as IADD3/IADD3.X pairs and the
+// +-EPS corrections as one IMAD.WIDE; see DESIGN.md section 5 for the instruction budget.
+#define BMI_LO(x) ((u32)(x))
+#define BMI_HI(x) ((u32)((x) >> 32))
+__device__ __forceinline__ u64 bmi_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+// canonical representative of a lazy value
+__device__ __forceinline__ u64 fcanon(u64 x) {
+    u32 t0, t1, c;
+    asm("add.cc.u32 %0,%3,0xFFFFFFFF; addc.cc.u32 %1,%4,0; addc.u32 %2,0,0;"
+        : "=r"(t0), "=r"(t1), "=r"(c) : "r"(BMI_LO(x)), "r"(BMI_HI(x)));
+    (void)t0; (void)t1;
+    return x + (u64)c * 0xFFFFFFFFu;          // x >= p  <=>  x + EPS carries; then x - p == x + EPS (mod 2^64)
+}
+// a + b, lazy result; at least one operand must be canonical (then the +EPS cannot carry again)
+__device__ __forceinline__ u64 fadd_l(u64 a, u64 b) {
+    u32 s0, s1, c;
+    asm("add.cc.u32 %0,%3,%5; addc.cc.u32 %1,%4,%6; addc.u32 %2,0,0;"
+        : "=r"(s0), "=r"(s1), "=r"(c) : "r"(BMI_LO(a)), "r"(BMI_HI(a)), "r"(BMI_LO(b)), "r"(BMI_HI(b)));
+    return bmi_pack(s0, s1) + (u64)c * 0xFFFFFFFFu;
+}
+// a - b, lazy result; b must be canonical (then the -EPS cannot borrow again)
+__device__ __forceinline__ u64 fsub_l(u64 a, u64 b) {
+    u32 s0, s1, m;
+    asm("sub.cc.u32 %0,%3,%5; subc.cc.u32 %1,%4,%6; subc.u32 %2,0,0;"
+        : "=r"(s0), "=r"(s1), "=r"(m) : "r"(BMI_LO(a)), "r"(BMI_HI(a)), "r"(BMI_LO(b)), "r"(BMI_HI(b)));
+    asm("sub.cc.u32 %0,%0,%2; subc.u32 %1,%1,0;" : "+r"(s0), "+r"(s1) : "r"(m));
+    return bmi_pack(s0, s1);
+}
+// a * b, lazy operands, lazy result
+__device__ __forceinline__ u64 fmul_l(u64 a, u64 b) {
+    const u32 a0 = BMI_LO(a), a1 = BMI_HI(a), b0 = BMI_LO(b), b1 = BMI_HI(b);
+    const u64 p00 = (u64)a0 * b0, p01 = (u64)a0 * b1, p10 = (u64)a1 * b0, p11 = (u64)a1 * b1;
+    u32 x0 = BMI_LO(p00), x1 = BMI_HI(p00), x2 = BMI_LO(p11), x3 = BMI_HI(p11);
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;" : "+r"(x1), "+r"(x2), "+r"(x3) : "r"(BMI_LO(p01)), "r"(BMI_HI(p01)));
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;" : "+r"(x1), "+r"(x2), "+r"(x3) : "r"(BMI_LO(p10)), "r"(BMI_HI(p10)));
+    // x = x0 + x1 2^32 + x2 2^64 + x3 2^96 = (x1:x0) - x3 + x2 * EPS
+    u32 r0, r1, m;
+    asm("sub.cc.u32 %0,%3,%5; subc.cc.u32 %1,%4,0; subc.u32 %2,0,0;" : "=r"(r0), "=r"(r1), "=r"(m) : "r"(x0), "r"(x1), "r"(x3));
+    asm("sub.cc.u32 %0,%0,%2; subc.u32 %1,%1,0;" : "+r"(r0), "+r"(r1) : "r"(m));
+    const u64 t1 = (u64)x2 * 0xFFFFFFFFu;      // < p, so the add below meets fadd_l's requirement
+    return fadd_l(bmi_pack(r0, r1), t1);
+}
+__device__ __forceinline__ u64 fmul_c(u64 a, u64 b) { return fcanon(fmul_l(a, b)); }
+#endif
+
 BMI_HD u64 fpow(u64 b, u64 e) {
     u64 r = 1;
     while (e) {

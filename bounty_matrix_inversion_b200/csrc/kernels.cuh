@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(NttCfg<L>::T) bsk_convert_kernel(const u64* __
     for (int q = 0; q < 16; q++) x[q] = s[q * C::T + tid];
     ntt_forward<L>(x, smem, tw, tid);
 #pragma unroll
-    for (int q = 0; q < 16; q++) d[q * C::T + tid] = fmul(x[q], ninv);
+    for (int q = 0; q < 16; q++) d[q * C::T + tid] = fmul_c(x[q], ninv);
 }
 
 // c = a * b mod (X^N + 1): exercises forward, pointwise and inverse transforms (self-test entry)
@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(NttCfg<L>::T) polymul_kernel(const u64* __rest
     ntt_forward<L>(x, smem, tw, tid);
     ntt_forward<L>(y, smem, tw, tid);
 #pragma unroll
-    for (int q = 0; q < 16; q++) x[q] = fmul(fmul(x[q], y[q]), ninv);
+    for (int q = 0; q < 16; q++) x[q] = fmul_l(fmul_l(x[q], y[q]), ninv);
     ntt_inverse<L>(x, smem, twi, tid);
 #pragma unroll
-    for (int q = 0; q < 16; q++) c[off + q * C::T + tid] = x[q];
+    for (int q = 0; q < 16; q++) c[off + q * C::T + tid] = fcanon(x[q]);
 }
 
 // ----------------------------------------------------------------------------
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(NttCfg<L>::T, 1) pbs_kernel(const PbsArgs a) {
                     const u64* row = g + (size_t)(c * l + (j - 1)) * 2 * N;
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
-                        sum0[q] = fadd(sum0[q], fmul(x[q], __ldg(row + q * T + tid)));
-                        sum1[q] = fadd(sum1[q], fmul(x[q], __ldg(row + N + q * T + tid)));
+                        sum0[q] = fadd_l(sum0[q], fmul_c(x[q], __ldg(row + q * T + tid)));
+                        sum1[q] = fadd_l(sum1[q], fmul_c(x[q], __ldg(row + N + q * T + tid)));
                     }
                 }
             }
@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(NttCfg<L>::T, 1) pbs_kernel(const PbsArgs a) {
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 const int idx = q * T + tid;
-                acc[idx] = fadd(acc[idx], sum0[q]);
-                acc[N + idx] = fadd(acc[N + idx], sum1[q]);
+                acc[idx] = fcanon(fadd_l(sum0[q], acc[idx]));          // acc stays canonical in shared memory
+                acc[N + idx] = fcanon(fadd_l(sum1[q], acc[N + idx]));
             }
             __syncthreads();
         }
@@ -137,24 +137,140 @@ __global__ void __launch_bounds__(NttCfg<L>::T, 1) pbs_kernel(const PbsArgs a) {
 }
 
 // ----------------------------------------------------------------------------
+// programmable bootstrap on a 2-CTA cluster: CTA c owns accumulator polynomial c (0 = mask, 1 = body).
+// Per CMUX each CTA decomposes and forward-transforms only ITS polynomial, multiplies it by both columns of
+// its GGSW rows, keeps the partial sum for its own output polynomial and pushes the partial sum for the
+// partner's polynomial straight into the partner's shared memory (DSMEM).  After the cluster barrier each CTA
+// adds what it received, inverse-transforms one polynomial and updates its accumulator: half the work and
+// half the registers of the single-CTA kernel per CTA, so one bootstrap finishes in about half the time.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ u32 cluster_rank() { u32 r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ u64* cluster_map(u64* p, u32 rank) {
+    u64 out;
+    asm("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((u64)p), "r"(rank));
+    return reinterpret_cast<u64*>(out);
+}
+
+// MINB = CTAs per SM the register budget is sized for: 1 keeps everything in registers (lowest latency, used
+// while a launch fits one wave); throughput_ctas_per_sm<L>() trades a few spills for twice the resident warps.
+template <int L>
+constexpr int throughput_ctas_per_sm() { return L <= 11 ? 4 : L == 12 ? 2 : 1; }
+
+template <int L, int MINB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
+    using C = NttCfg<L>;
+    constexpr int N = C::N, T = C::T;
+    extern __shared__ u64 smem[];
+    u64* acc = smem;                  // [N] this CTA's accumulator polynomial
+    u64* buf = smem + N;              // [N] transform exchange buffer (swizzled)
+    u64* recv = smem + 2 * N;         // [N] partial sums pushed by the partner CTA
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N);
+    const int tid = threadIdx.x;
+    const u32 me = cluster_rank(), other = me ^ 1;
+    u64* peer_recv = cluster_map(recv, other);
+    const int n = a.n, bl = a.bl, l = a.l, tot = bl * l;
+    const int total = a.njobs * a.batch;
+
+    cluster_arrive();                 // opens the "recv is free" barrier of the first CMUX
+    for (int f = blockIdx.x >> 1; f < total; f += gridDim.x >> 1) {
+        const int q0 = f / a.batch, b0 = f - q0 * a.batch;
+        const u64* in = a.small + ((size_t)a.job_in[q0] * a.batch + b0) * (n + 1);
+        const u64* lut = a.luts + (size_t)a.job_lut[q0] * N;
+        u64* out = a.out + ((size_t)a.job_out[q0] * a.batch + b0) * (N + 1);
+
+        __syncthreads();
+        for (int i = tid; i < n; i += T) rot[i] = (unsigned short)modswitch(in[i], L);
+        {
+            const u32 r0 = (2 * N - modswitch(in[n], L)) & (2 * N - 1);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int idx = q * T + tid;
+                const u32 u = (idx + 2 * N - r0) & (2 * N - 1);
+                acc[idx] = me == 0 ? 0 : (u < N ? lut[u] : fneg(lut[u - N]));
+            }
+        }
+        __syncthreads();
+
+        for (int i = 0; i < n; i++) {
+            const u32 at = rot[i];
+            if (at == 0) continue;
+            u64 own[16], oth[16];
+#pragma unroll
+            for (int q = 0; q < 16; q++) { own[q] = 0; oth[q] = 0; }
+            const u64* g = a.bsk_hat + ((size_t)i * (2 * l) + me * l) * 2 * N;
+            for (int j = 1; j <= l; j++) {
+                u64 x[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int idx = q * T + tid;
+                    const u32 u = (idx + 2 * N - at) & (2 * N - 1);
+                    const u64 r = u < N ? acc[u] : fneg(acc[u - N]);
+                    x[q] = digit_of(round_top(fsub(r, acc[idx]), tot), bl, l, j);
+                }
+                ntt_forward<L>(x, buf, a.tw, tid);
+                const u64* row = g + (size_t)(j - 1) * 2 * N;
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    own[q] = fadd_l(own[q], fmul_c(x[q], __ldg(row + me * N + q * T + tid)));
+                    oth[q] = fadd_l(oth[q], fmul_c(x[q], __ldg(row + other * N + q * T + tid)));
+                }
+            }
+            cluster_wait();           // partner has consumed what I pushed for the previous CMUX
+#pragma unroll
+            for (int q = 0; q < 16; q++) peer_recv[q * T + tid] = fcanon(oth[q]);
+            cluster_arrive();         // my push is visible ...
+            cluster_wait();           // ... and so is the partner's
+#pragma unroll
+            for (int q = 0; q < 16; q++) own[q] = fadd_l(own[q], recv[q * T + tid]);
+            cluster_arrive();         // recv may be overwritten again
+            ntt_inverse<L>(own, buf, a.twi, tid);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int idx = q * T + tid;
+                acc[idx] = fcanon(fadd_l(own[q], acc[idx]));
+            }
+            __syncthreads();
+        }
+
+        if (me == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const int t = q * T + tid;
+                out[t] = t == 0 ? acc[0] : fneg(acc[N - t]);
+            }
+        } else if (tid == 0) {
+            out[N] = acc[0];
+        }
+    }
+    cluster_wait();                   // balance the last arrive before exiting
+}
+
+// ----------------------------------------------------------------------------
 // keyswitch big (kN) -> small (n): out = (0, b) - sum_i sum_j digit_ij * ksk[i][j]
-// CTA = 128 output columns x JT ciphertexts; digits staged in shared memory per chunk.
+// CTA = 128 output columns x KS_JT ciphertexts x one slice of the kN input coefficients (blockIdx.z).
+// Digits of a 64-coefficient chunk are staged in shared memory; every keyswitch-key word read from
+// L2/HBM is used for KS_JT ciphertexts.  Products accumulate unreduced in 128 bits.  With more than one
+// slice the per-slice sums go to `partial` and keyswitch_finish_kernel folds them.
 constexpr int KS_COLS = 128, KS_JT = 8, KS_CHUNK = 64;
 
 __global__ void __launch_bounds__(KS_COLS) keyswitch_kernel(const u64* __restrict__ in, const u64* __restrict__ ksk,
-                                                            u64* __restrict__ out, int M, int kN, int n, int bl, int l) {
+                                                            u64* __restrict__ out, u64* __restrict__ partial, int M, int kN,
+                                                            int n, int bl, int l, int slice) {
     extern __shared__ int dg[];   // [KS_CHUNK][l][KS_JT]
     const int tid = threadIdx.x, t = blockIdx.x * KS_COLS + tid;
     const int job0 = blockIdx.y * KS_JT;
     const int njob = min(KS_JT, M - job0);
     const int tot = bl * l;
     const bool live = t <= n;
+    const int i_begin = blockIdx.z * slice, i_end = min(kN, i_begin + slice);
     u64 lo[KS_JT], hi[KS_JT];
 #pragma unroll
     for (int jb = 0; jb < KS_JT; jb++) { lo[jb] = 0; hi[jb] = 0; }
 
-    for (int i0 = 0; i0 < kN; i0 += KS_CHUNK) {
-        const int ci = min(KS_CHUNK, kN - i0);
+    for (int i0 = i_begin; i0 < i_end; i0 += KS_CHUNK) {
+        const int ci = min(KS_CHUNK, i_end - i0);
         __syncthreads();
         for (int e = tid; e < KS_CHUNK * KS_JT; e += KS_COLS) {
             const int jb = e / KS_CHUNK, ii = e % KS_CHUNK;
@@ -171,21 +287,22 @@ __global__ void __launch_bounds__(KS_COLS) keyswitch_kernel(const u64* __restric
         }
         __syncthreads();
         if (live) {
-            for (int ii = 0; ii < ci; ii++) {
-                for (int j = 0; j < l; j++) {
-                    const u64 kv = __ldg(ksk + ((size_t)(i0 + ii) * l + j) * (n + 1) + t);
-                    const u64 kneg = fneg(kv);
-                    const int* d = dg + (ii * l + j) * KS_JT;
+            const u64* kp = ksk + (size_t)i0 * l * (n + 1) + t;
+            const int rows = ci * l;
+#pragma unroll 4
+            for (int r = 0; r < rows; r++) {
+                const u64 kv = __ldg(kp + (size_t)r * (n + 1));
+                const u64 kneg = fneg(kv);
+                const int* d = dg + r * KS_JT;
 #pragma unroll
-                    for (int jb = 0; jb < KS_JT; jb++) {
-                        const int sd = d[jb];
-                        if (sd == 0) continue;
-                        const u64 m = sd > 0 ? (u64)sd : (u64)(-sd);
-                        const u64 v = sd > 0 ? kv : kneg;
-                        const u64 pl = m * v, ph = __umul64hi(m, v);
-                        lo[jb] += pl;
-                        hi[jb] += ph + (lo[jb] < pl);
-                    }
+                for (int jb = 0; jb < KS_JT; jb++) {
+                    const int sd = d[jb];
+                    if (sd == 0) continue;
+                    const u64 m = sd > 0 ? (u64)sd : (u64)(-sd);
+                    const u64 v = sd > 0 ? kv : kneg;
+                    const u64 pl = m * v, ph = __umul64hi(m, v);
+                    lo[jb] += pl;
+                    hi[jb] += ph + (lo[jb] < pl);
                 }
             }
         }
@@ -194,10 +311,26 @@ __global__ void __launch_bounds__(KS_COLS) keyswitch_kernel(const u64* __restric
 #pragma unroll
         for (int jb = 0; jb < KS_JT; jb++) {
             if (jb >= njob) break;
-            const u64 base = t == n ? in[(size_t)(job0 + jb) * (kN + 1) + kN] : 0;
-            out[(size_t)(job0 + jb) * (n + 1) + t] = fsub(base, freduce128(lo[jb], hi[jb]));
+            const u64 sum = freduce128(lo[jb], hi[jb]);
+            if (gridDim.z == 1) {
+                const u64 base = t == n ? in[(size_t)(job0 + jb) * (kN + 1) + kN] : 0;
+                out[(size_t)(job0 + jb) * (n + 1) + t] = fsub(base, sum);
+            } else {
+                partial[((size_t)blockIdx.z * M + job0 + jb) * (n + 1) + t] = sum;
+            }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) keyswitch_finish_kernel(const u64* __restrict__ in, const u64* __restrict__ partial,
+                                                               u64* __restrict__ out, int M, int kN, int n, int slices) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)M * (n + 1)) return;
+    const int job = (int)(e / (n + 1)), t = (int)(e % (n + 1));
+    u64 s = 0;
+    for (int z = 0; z < slices; z++) s = fadd(s, partial[(size_t)z * M * (n + 1) + e]);
+    const u64 base = t == n ? in[(size_t)job * (kN + 1) + kN] : 0;
+    out[e] = fsub(base, s);
 }
 
 // ----------------------------------------------------------------------------

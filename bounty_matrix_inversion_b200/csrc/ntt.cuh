@@ -10,6 +10,8 @@
 // Forward = Cooley-Tukey with merged psi twiddles (natural order in, bit-reversed out);
 // inverse = Gentleman-Sande (bit-reversed in, natural out, NOT scaled by 1/N: the
 // bootstrapping key is pre-scaled instead).  tw[m + i] = psi^brv(m + i).
+// Values inside a transform are "lazy" (any u64 congruent to the element, see field.cuh): inputs may be
+// lazy, outputs are lazy; only the multiplied operand of each butterfly is made canonical.
 #pragma once
 #include "field.cuh"
 
@@ -38,15 +40,27 @@ __device__ __forceinline__ int slot_index(int p, int q, int tid) {
     }
 }
 
+// Bits contributed by the thread (q = 0) and by the register slot are disjoint, and swz() is linear over
+// XOR, so swz(index) = swz(thread part) ^ swz(slot part): one XOR per access, the slot part a constant.
+template <int L>
+__device__ __forceinline__ constexpr int slot_bits(int p, int q) {
+    using C = NttCfg<L>;
+    if (p < C::FULL) return q << (L - 4 * p - 4);
+    return (((q >> C::R) * C::T) << C::R) | (q & ((1 << C::R) - 1));
+}
+__device__ __forceinline__ constexpr int swz_c(int i) { return i ^ (((i >> 4) ^ (i >> 8) ^ (i >> 12)) & 15); }
+
 template <int L>
 __device__ __forceinline__ void store_pass(const u64 (&x)[16], u64* buf, int p, int tid) {
+    const int sb = swz(slot_index<L>(p, 0, tid));
 #pragma unroll
-    for (int q = 0; q < 16; q++) buf[swz(slot_index<L>(p, q, tid))] = x[q];
+    for (int q = 0; q < 16; q++) buf[sb ^ swz_c(slot_bits<L>(p, q))] = x[q];
 }
 template <int L>
 __device__ __forceinline__ void load_pass(u64 (&x)[16], const u64* buf, int p, int tid) {
+    const int sb = swz(slot_index<L>(p, 0, tid));
 #pragma unroll
-    for (int q = 0; q < 16; q++) x[q] = buf[swz(slot_index<L>(p, q, tid))];
+    for (int q = 0; q < 16; q++) x[q] = buf[sb ^ swz_c(slot_bits<L>(p, q))];
 }
 
 // stages of pass p on registers; INV selects the Gentleman-Sande form and reversed stage order
@@ -67,12 +81,13 @@ __device__ __forceinline__ void pass_compute(u64 (&x)[16], const u64* __restrict
                 const u64 w = __ldg(tw + base + (q >> (4 - d)));
                 const u64 u = x[q], v = x[q + half];
                 if (!INV) {
-                    const u64 t = fmul(v, w);
-                    x[q] = fadd(u, t);
-                    x[q + half] = fsub(u, t);
+                    const u64 t = fmul_c(v, w);
+                    x[q] = fadd_l(u, t);
+                    x[q + half] = fsub_l(u, t);
                 } else {
-                    x[q] = fadd(u, v);
-                    x[q + half] = fmul(fsub(u, v), w);
+                    const u64 vc = fcanon(v);
+                    x[q] = fadd_l(u, vc);
+                    x[q + half] = fmul_l(fsub_l(u, vc), w);
                 }
             }
         }
@@ -89,12 +104,13 @@ __device__ __forceinline__ void pass_compute(u64 (&x)[16], const u64* __restrict
                 const u64 w = __ldg(tw + (1 << (L - R + d)) + ((g * C::T + tid) << d) + (e >> (R - d)));
                 const u64 u = x[q], v = x[q + half];
                 if (!INV) {
-                    const u64 t = fmul(v, w);
-                    x[q] = fadd(u, t);
-                    x[q + half] = fsub(u, t);
+                    const u64 t = fmul_c(v, w);
+                    x[q] = fadd_l(u, t);
+                    x[q + half] = fsub_l(u, t);
                 } else {
-                    x[q] = fadd(u, v);
-                    x[q + half] = fmul(fsub(u, v), w);
+                    const u64 vc = fcanon(v);
+                    x[q] = fadd_l(u, vc);
+                    x[q + half] = fmul_l(fsub_l(u, vc), w);
                 }
             }
         }

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "bmi_ctx_load_ksk": (C.c_int, [C.c_void_p, U64P]),
     "bmi_ctx_load_luts": (C.c_int, [C.c_void_p, U64P, C.c_int32]),
     "bmi_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "bmi_ctx_set_pbs_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "bmi_lincomb": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_void_p]),
     "bmi_keyswitch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bmi_pbs": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p]),
@@ -153,6 +154,10 @@ class Engine:
         luts = _u64(luts).reshape(-1, self.params.N)
         _check(lib().bmi_ctx_load_luts(self._h, _p(luts), luts.shape[0]))
         self.n_luts = luts.shape[0]
+
+    def set_pbs_mode(self, mode: int):
+        """0 automatic, 1 always the 2-CTA cluster kernel, 2 always the single-CTA kernel"""
+        _check(lib().bmi_ctx_set_pbs_mode(self._h, mode))
 
     @property
     def launch_count(self) -> int:

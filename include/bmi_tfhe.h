@@ -68,6 +68,9 @@ int bmi_ctx_load_bsk(bmi_ctx* ctx, const uint64_t* h_bsk);   /* upload + convert
 int bmi_ctx_load_ksk(bmi_ctx* ctx, const uint64_t* h_ksk);
 int bmi_ctx_load_luts(bmi_ctx* ctx, const uint64_t* h_luts, int32_t n_luts);   /* [n_luts][N] accumulator polynomials */
 int64_t bmi_ctx_launch_count(const bmi_ctx* ctx);            /* kernels launched by this context so far */
+/* bootstrap kernel choice: 0 = automatic (CTA pair per ciphertext; register budget picked per launch size),
+ * 1 = CTA pair, all-in-registers build (lowest latency), 2 = one CTA per ciphertext */
+int bmi_ctx_set_pbs_mode(bmi_ctx* ctx, int32_t mode);
 
 /* out[j][b] = sum_t coef[t] * vals[idx[t]][b] + konst[j], rows of k*N+1 words.
  * CSR: d_row_ptr [njobs+1] int32, d_idx int32 (row of d_vals before batch expansion), d_coef uint64 field elements */

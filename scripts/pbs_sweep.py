@@ -30,7 +30,8 @@ def main():
         w = 3
         luts = np.stack([PR.lut_polynomial([PR.encode(t, w) for t in range(8)], w, prm.N)])
         eng.load_luts(luts)
-        for count in (1, 148, 296, 592):
+        for mode, count in [(m, c) for m in (1, 2) for c in (1, 74, 148, 296, 592)]:
+            eng.set_pbs_mode(mode)
             cts = keys.encrypt([PR.encode(i % 8, w) for i in range(min(count, 16))])
             cts = np.tile(cts, (count // len(cts) + 1, 1))[:count]
             big = torch.from_numpy(cts.view(np.int64)).cuda()
@@ -48,7 +49,7 @@ def main():
                 torch.cuda.synchronize()
             ks_ms, pbs_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
             dec = [PR.decode(int(p), w) for p in keys.phase(out[:4].cpu().numpy().view(np.uint64))]
-            print(json.dumps({"set": prm.name, "count": count, "ks_ms": round(ks_ms, 3), "pbs_ms": round(pbs_ms, 3),
+            print(json.dumps({"set": prm.name, "mode": mode, "count": count, "ks_ms": round(ks_ms, 3), "pbs_ms": round(pbs_ms, 3),
                               "pbs_per_s": round(count / (pbs_ms + ks_ms) * 1e3, 1), "dec": dec,
                               "keygen_s": round(t_keys, 2), "load_s": round(t_load, 2)}), flush=True)
         eng.close()
