@@ -57,10 +57,12 @@ class Executor:
         self.max_ks = max((len(l.konst) for l in lv), default=1)
         self.max_pbs = max((len(l.job_ks) for l in lv), default=1)
         self._batch = 0
+        self.stream = None           # torch.cuda.Stream for every launch of this executor (None = current stream)
         self.profile = None          # list of (start event, end event, jobs) around every PBS launch when profiling
 
-    def collect_profile(self):
-        """PBS-kernel time measured with CUDA events on the launching stream, and the algorithmic work it covers"""
+    def collect_profile(self, origin=None):
+        """PBS-kernel time measured with CUDA events on the launching stream, and the algorithmic work it covers;
+        with `origin` (an event recorded before the region) also the [start, end] offsets of every launch in ms"""
         torch.cuda.synchronize(self.dev)
         p = self.params
         prof = self.profile or []
@@ -69,8 +71,11 @@ class Executor:
         per_pbs_bytes = p.bsk_bytes() + (p.n + 1) * 8 + p.N * 8 + (p.big_dim + 1) * 8
         butterflies = (p.k + 1) * (p.bsk_l + 1) * (p.N // 2) * p.logN
         per_pbs_int = p.n * (butterflies * 26 + (p.k + 1) ** 2 * p.bsk_l * p.N * 22 + (p.k + 1) * p.bsk_l * p.N * 12)
-        return {"pbs_ms": ms, "pbs_launches": len(prof), "pbs_jobs": jobs, "alg_bytes": jobs * per_pbs_bytes,
-                "int_ops": jobs * per_pbs_int}
+        out = {"pbs_ms": ms, "pbs_launches": len(prof), "pbs_jobs": jobs, "alg_bytes": jobs * per_pbs_bytes,
+               "int_ops": jobs * per_pbs_int}
+        if origin is not None:
+            out["intervals"] = [(origin.elapsed_time(a), origin.elapsed_time(b)) for a, b, _ in prof]
+        return out
 
     def _ensure(self, batch):
         if batch == self._batch:
@@ -105,10 +110,14 @@ class Executor:
         for li in range(len(prog.levels)):
             self._level(li, batch)
         eng.lincomb(self.vals, self.d_out_ptr, self.d_out_idx, self.d_out_coef, self.d_out_konst, self.outs,
-                    len(prog.out_konst), batch)
+                    len(prog.out_konst), batch, stream=self._s())
+
+    def _s(self):
+        return self.stream if self.stream is not None else torch.cuda.current_stream(self.dev)
 
     def _level(self, li, batch):
         eng = self.eng
+        st = self._s()
         k0, k1 = self.ks_off[li], self.ks_off[li + 1]
         p0, p1 = self.pbs_off[li], self.pbs_off[li + 1]
         n_ks, n_pbs = int(k1 - k0), int(p1 - p0)
@@ -121,16 +130,16 @@ class Executor:
         konst = self.d_konst[k0:k1]
         job_ks, job_lut, job_out = self.d_job_ks[p0:p1], self.d_job_lut[p0:p1], self.d_job_out[p0:p1]
         if self.world == 1:
-            eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch)
-            eng.keyswitch(self.ks_in, self.small, n_ks * batch)
+            eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch, stream=st)
+            eng.keyswitch(self.ks_in, self.small, n_ks * batch, stream=st)
             if self.profile is not None:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch)
-                b.record()
+                a.record(st)
+                eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch, stream=st)
+                b.record(st)
                 self.profile.append((a, b, n_pbs * batch))
             else:
-                eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch)
+                eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch, stream=st)
             return
         self._level_sharded(li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs)
 
@@ -142,12 +151,13 @@ class Executor:
         per = (n_pbs + self.world - 1) // self.world
         lo, hi = min(self.rank * per, n_pbs), min((self.rank + 1) * per, n_pbs)
         # every rank forms all keyswitch inputs it needs; for simplicity all rows (cheap next to the bootstraps)
-        eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch)
-        eng.keyswitch(self.ks_in, self.small, n_ks * batch)
+        st = self._s()
+        eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch, stream=st)
+        eng.keyswitch(self.ks_in, self.small, n_ks * batch, stream=st)
         stage = self.stage[: per * self.world]
         if hi > lo:
             local_out = torch.arange(lo, hi, dtype=torch.int32, device=self.dev)
-            eng.pbs(self.small, job_ks[lo:hi], job_lut[lo:hi], local_out, stage, hi - lo, batch)
+            eng.pbs(self.small, job_ks[lo:hi], job_lut[lo:hi], local_out, stage, hi - lo, batch, stream=st)
         mine = stage[self.rank * per: (self.rank + 1) * per]
         dist.all_gather_into_tensor(stage, mine.clone(), group=self.group)
         self.vals.index_copy_(0, job_out.long(), stage[:n_pbs])
