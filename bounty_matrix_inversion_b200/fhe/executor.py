@@ -21,16 +21,24 @@ def _field(vals, scale=1):
     return out.view(np.int64)
 
 
+def shard_bounds(n_jobs: int, rank: int, world: int):
+    """contiguous share of a level's lookups owned by `rank`: (rows per rank in the gather buffer, first, last+1)"""
+    per = (n_jobs + world - 1) // world
+    return per, min(rank * per, n_jobs), min((rank + 1) * per, n_jobs)
+
+
 class Executor:
     def __init__(self, program: Program, params: PR.TfheParams, engine: Engine, device: int = 0,
-                 rank: int = 0, world: int = 1, group=None):
+                 rank: int = 0, world: int = 1, group=None, torch_device=None):
+        """engine: anything with load_luts / lincomb / keyswitch / pbs taking torch tensors (native.Engine on a GPU;
+        the CPU tests of the multi-rank plumbing inject a clear-text stand-in).  rank/world/group: level sharding."""
         self.prog, self.params, self.eng = program, params, engine
-        self.dev = torch.device("cuda", device)
+        self.dev = torch.device("cuda", device) if torch_device is None else torch.device(torch_device)
         self.rank, self.world, self.group = rank, world, group
-        W1 = params.big_dim + 1
+        W1 = getattr(engine, "words", params.big_dim + 1)
         self.W1 = W1
-        engine.load_luts(program.lut_polynomials(params.N))
-        scale = PR.delta(program.width)
+        engine.load_luts(program.lut_polynomials(params.N) if not getattr(engine, "clear", False) else program.tables)
+        scale = PR.delta(program.width) if not getattr(engine, "clear", False) else 1
         lv = program.levels
 
         def cat(arrs, dtype):
@@ -63,7 +71,8 @@ class Executor:
     def collect_profile(self, origin=None):
         """PBS-kernel time measured with CUDA events on the launching stream, and the algorithmic work it covers;
         with `origin` (an event recorded before the region) also the [start, end] offsets of every launch in ms"""
-        torch.cuda.synchronize(self.dev)
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
         p = self.params
         prof = self.profile or []
         ms = sum(a.elapsed_time(b) for a, b, _ in prof)
@@ -83,11 +92,12 @@ class Executor:
         p = self.params
         self.vals = torch.zeros((self.prog.n_slots, batch, self.W1), dtype=torch.int64, device=self.dev)
         self.ks_in = torch.empty((self.max_ks * batch, self.W1), dtype=torch.int64, device=self.dev)
-        self.small = torch.empty((self.max_ks * batch, p.n + 1), dtype=torch.int64, device=self.dev)
+        self.small = torch.empty((self.max_ks * batch, getattr(self.eng, "small_words", p.n + 1)), dtype=torch.int64, device=self.dev)
         n_out = len(self.prog.out_konst)
         self.outs = torch.empty((n_out, batch, self.W1), dtype=torch.int64, device=self.dev)
         if self.world > 1:
-            self.stage = torch.empty((self.max_pbs, batch, self.W1), dtype=torch.int64, device=self.dev)
+            rows = shard_bounds(self.max_pbs, 0, self.world)[0] * self.world       # padded so every rank owns `per` rows
+            self.stage = torch.empty((rows, batch, self.W1), dtype=torch.int64, device=self.dev)
         self._batch = batch
 
     def run(self, input_cts: np.ndarray) -> np.ndarray:
@@ -113,6 +123,8 @@ class Executor:
                     len(prog.out_konst), batch, stream=self._s())
 
     def _s(self):
+        if self.dev.type != "cuda":
+            return None
         return self.stream if self.stream is not None else torch.cuda.current_stream(self.dev)
 
     def _level(self, li, batch):
@@ -148,8 +160,7 @@ class Executor:
     def _level_sharded(self, li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs):
         import torch.distributed as dist
         eng = self.eng
-        per = (n_pbs + self.world - 1) // self.world
-        lo, hi = min(self.rank * per, n_pbs), min((self.rank + 1) * per, n_pbs)
+        per, lo, hi = shard_bounds(n_pbs, self.rank, self.world)
         # every rank forms all keyswitch inputs it needs; for simplicity all rows (cheap next to the bootstraps)
         st = self._s()
         eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch, stream=st)
