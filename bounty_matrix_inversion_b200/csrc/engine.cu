@@ -49,9 +49,11 @@ size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c-
 template <int L>
 int setup_attrs(const bmi_ctx* c) {
     CK(cudaFuncSetAttribute(pbs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, throughput_ctas_per_sm<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)pbs_smem(c)));
+    constexpr int TP = throughput_ctas_per_sm<L>();
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, TP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, TP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
     CK(cudaFuncSetAttribute(bsk_convert_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(polymul_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     return BMI_OK;
@@ -74,13 +76,18 @@ int launch_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) {
     } else {
         // CTA pair per ciphertext.  While the launch fits the resident CTA pairs of the all-in-registers build,
         // latency wins; beyond one wave the higher-occupancy build does.
+        constexpr int TP = throughput_ctas_per_sm<L>();
+        const bool one = a.l == 1;
         int resident = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, 1>, NttCfg<L>::T, pbs_smem(c));
+        if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, 1, true>, NttCfg<L>::T, pbs_smem(c));
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, 1, false>, NttCfg<L>::T, pbs_smem(c));
         const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
-        if (c->pbs_mode == 1 || total <= one_wave)
-            pbs_cluster_kernel<L, 1><<<2 * grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);
-        else
-            pbs_cluster_kernel<L, throughput_ctas_per_sm<L>()><<<2 * grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);
+        const bool latency = c->pbs_mode == 1 || total <= one_wave;
+        const dim3 g2(2 * grid), blk(NttCfg<L>::T);
+        if (latency && one) pbs_cluster_kernel<L, 1, true><<<g2, blk, pbs_smem(c), st>>>(a);
+        else if (latency) pbs_cluster_kernel<L, 1, false><<<g2, blk, pbs_smem(c), st>>>(a);
+        else if (one) pbs_cluster_kernel<L, TP, true><<<g2, blk, pbs_smem(c), st>>>(a);
+        else pbs_cluster_kernel<L, TP, false><<<g2, blk, pbs_smem(c), st>>>(a);
     }
     c->launches++;
     CK(cudaGetLastError());

@@ -61,7 +61,7 @@ __device__ __forceinline__ u64 bmi_pack(u32 lo, u32 hi) { return ((u64)hi << 32)
 // canonical representative of a lazy value
 __device__ __forceinline__ u64 fcanon(u64 x) {
     u32 t0, t1, c;
-    asm("add.cc.u32 %0,%3,0xFFFFFFFF; addc.cc.u32 %1,%4,0; addc.u32 %2,0,0;"
+    asm("add.cc.u32 %0,%3,0xFFFFFFFF; addc.cc.u32 %1,%4,0; madc.lo.u32 %2,0,0,0;"
         : "=r"(t0), "=r"(t1), "=r"(c) : "r"(BMI_LO(x)), "r"(BMI_HI(x)));
     (void)t0; (void)t1;
     return x + (u64)c * 0xFFFFFFFFu;          // x >= p  <=>  x + EPS carries; then x - p == x + EPS (mod 2^64)
@@ -69,7 +69,7 @@ __device__ __forceinline__ u64 fcanon(u64 x) {
 // a + b, lazy result; at least one operand must be canonical (then the +EPS cannot carry again)
 __device__ __forceinline__ u64 fadd_l(u64 a, u64 b) {
     u32 s0, s1, c;
-    asm("add.cc.u32 %0,%3,%5; addc.cc.u32 %1,%4,%6; addc.u32 %2,0,0;"
+    asm("add.cc.u32 %0,%3,%5; addc.cc.u32 %1,%4,%6; madc.lo.u32 %2,0,0,0;"
         : "=r"(s0), "=r"(s1), "=r"(c) : "r"(BMI_LO(a)), "r"(BMI_HI(a)), "r"(BMI_LO(b)), "r"(BMI_HI(b)));
     return bmi_pack(s0, s1) + (u64)c * 0xFFFFFFFFu;
 }
@@ -84,10 +84,12 @@ __device__ __forceinline__ u64 fsub_l(u64 a, u64 b) {
 // a * b, lazy operands, lazy result
 __device__ __forceinline__ u64 fmul_l(u64 a, u64 b) {
     const u32 a0 = BMI_LO(a), a1 = BMI_HI(a), b0 = BMI_LO(b), b1 = BMI_HI(b);
-    const u64 p00 = (u64)a0 * b0, p01 = (u64)a0 * b1, p10 = (u64)a1 * b0, p11 = (u64)a1 * b1;
-    u32 x0 = BMI_LO(p00), x1 = BMI_HI(p00), x2 = BMI_LO(p11), x3 = BMI_HI(p11);
-    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;" : "+r"(x1), "+r"(x2), "+r"(x3) : "r"(BMI_LO(p01)), "r"(BMI_HI(p01)));
-    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;" : "+r"(x1), "+r"(x2), "+r"(x3) : "r"(BMI_LO(p10)), "r"(BMI_HI(p10)));
+    // partial products chained through the 64-bit addend of IMAD.WIDE (no carry can be lost: each sum < 2^64)
+    const u64 p00 = (u64)a0 * b0;
+    const u64 t = (u64)a0 * b1 + (p00 >> 32);
+    const u64 t2 = (u64)a1 * b0 + (u64)BMI_LO(t);
+    const u64 h = (u64)a1 * b1 + (t >> 32) + (t2 >> 32);
+    const u32 x0 = BMI_LO(p00), x1 = BMI_LO(t2), x2 = BMI_LO(h), x3 = BMI_HI(h);
     // x = x0 + x1 2^32 + x2 2^64 + x3 2^96 = (x1:x0) - x3 + x2 * EPS
     u32 r0, r1, m;
     asm("sub.cc.u32 %0,%3,%5; subc.cc.u32 %1,%4,0; subc.u32 %2,0,0;" : "=r"(r0), "=r"(r1), "=r"(m) : "r"(x0), "r"(x1), "r"(x3));

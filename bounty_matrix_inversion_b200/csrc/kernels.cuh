@@ -158,7 +158,9 @@ __device__ __forceinline__ u64* cluster_map(u64* p, u32 rank) {
 template <int L>
 constexpr int throughput_ctas_per_sm() { return L <= 11 ? 4 : L == 12 ? 2 : 1; }
 
-template <int L, int MINB>
+// ONE_LEVEL: l == 1 (every 128-bit parameter set this engine selects): the partner's partial sum is a single
+// product per coefficient and goes straight to DSMEM instead of being accumulated in 32 registers.
+template <int L, int MINB, bool ONE_LEVEL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
     using C = NttCfg<L>;
     constexpr int N = C::N, T = C::T;
@@ -196,30 +198,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L>::T, MINB) 
         for (int i = 0; i < n; i++) {
             const u32 at = rot[i];
             if (at == 0) continue;
-            u64 own[16], oth[16];
-#pragma unroll
-            for (int q = 0; q < 16; q++) { own[q] = 0; oth[q] = 0; }
+            u64 own[16];
             const u64* g = a.bsk_hat + ((size_t)i * (2 * l) + me * l) * 2 * N;
-            for (int j = 1; j <= l; j++) {
+            if (ONE_LEVEL) {
                 u64 x[16];
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const int idx = q * T + tid;
                     const u32 u = (idx + 2 * N - at) & (2 * N - 1);
                     const u64 r = u < N ? acc[u] : fneg(acc[u - N]);
-                    x[q] = digit_of(round_top(fsub(r, acc[idx]), tot), bl, l, j);
+                    x[q] = digit_of(round_top(fsub(r, acc[idx]), tot), bl, 1, 1);
                 }
                 ntt_forward<L>(x, buf, a.tw, tid);
-                const u64* row = g + (size_t)(j - 1) * 2 * N;
+                cluster_wait();       // partner has consumed what I pushed for the previous CMUX
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
-                    own[q] = fadd_l(own[q], fmul_c(x[q], __ldg(row + me * N + q * T + tid)));
-                    oth[q] = fadd_l(oth[q], fmul_c(x[q], __ldg(row + other * N + q * T + tid)));
+                    peer_recv[q * T + tid] = fmul_c(x[q], __ldg(g + other * N + q * T + tid));
+                    own[q] = fmul_l(x[q], __ldg(g + me * N + q * T + tid));
                 }
-            }
-            cluster_wait();           // partner has consumed what I pushed for the previous CMUX
+            } else {
+                u64 oth[16];
 #pragma unroll
-            for (int q = 0; q < 16; q++) peer_recv[q * T + tid] = fcanon(oth[q]);
+                for (int q = 0; q < 16; q++) { own[q] = 0; oth[q] = 0; }
+                for (int j = 1; j <= l; j++) {
+                    u64 x[16];
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const int idx = q * T + tid;
+                        const u32 u = (idx + 2 * N - at) & (2 * N - 1);
+                        const u64 r = u < N ? acc[u] : fneg(acc[u - N]);
+                        x[q] = digit_of(round_top(fsub(r, acc[idx]), tot), bl, l, j);
+                    }
+                    ntt_forward<L>(x, buf, a.tw, tid);
+                    const u64* row = g + (size_t)(j - 1) * 2 * N;
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        own[q] = fadd_l(own[q], fmul_c(x[q], __ldg(row + me * N + q * T + tid)));
+                        oth[q] = fadd_l(oth[q], fmul_c(x[q], __ldg(row + other * N + q * T + tid)));
+                    }
+                }
+                cluster_wait();       // partner has consumed what I pushed for the previous CMUX
+#pragma unroll
+                for (int q = 0; q < 16; q++) peer_recv[q * T + tid] = fcanon(oth[q]);
+            }
             cluster_arrive();         // my push is visible ...
             cluster_wait();           // ... and so is the partner's
 #pragma unroll
