@@ -81,19 +81,24 @@ __device__ __forceinline__ u64 fsub_l(u64 a, u64 b) {
     asm("sub.cc.u32 %0,%0,%2; subc.u32 %1,%1,0;" : "+r"(s0), "+r"(s1) : "r"(m));
     return bmi_pack(s0, s1);
 }
-// a * b, lazy operands, lazy result
+// a * b, lazy operands, lazy result.  One PTX block: four 32x32->64 partial products (IMAD.WIDE), merged by two
+// carry chains that ptxas folds into 3-input IADD3s, then x = x0 + x1 2^32 + x2 2^64 + x3 2^96
+//   = (x1:x0) - x3 + x2 * EPS  (mod p)
 __device__ __forceinline__ u64 fmul_l(u64 a, u64 b) {
-    const u32 a0 = BMI_LO(a), a1 = BMI_HI(a), b0 = BMI_LO(b), b1 = BMI_HI(b);
-    // partial products chained through the 64-bit addend of IMAD.WIDE (no carry can be lost: each sum < 2^64)
-    const u64 p00 = (u64)a0 * b0;
-    const u64 t = (u64)a0 * b1 + (p00 >> 32);
-    const u64 t2 = (u64)a1 * b0 + (u64)BMI_LO(t);
-    const u64 h = (u64)a1 * b1 + (t >> 32) + (t2 >> 32);
-    const u32 x0 = BMI_LO(p00), x1 = BMI_LO(t2), x2 = BMI_LO(h), x3 = BMI_HI(h);
-    // x = x0 + x1 2^32 + x2 2^64 + x3 2^96 = (x1:x0) - x3 + x2 * EPS
-    u32 r0, r1, m;
-    asm("sub.cc.u32 %0,%3,%5; subc.cc.u32 %1,%4,0; subc.u32 %2,0,0;" : "=r"(r0), "=r"(r1), "=r"(m) : "r"(x0), "r"(x1), "r"(x3));
-    asm("sub.cc.u32 %0,%0,%2; subc.u32 %1,%1,0;" : "+r"(r0), "+r"(r1) : "r"(m));
+    u32 r0, r1, x2, m;
+    asm("{ .reg .u32 a0,a1,b0,b1,l0,h0,l1,h1,l2,h2,l3,h3,y1,y2,y3; .reg .u64 p;\n"
+        "mov.b64 {a0,a1},%4; mov.b64 {b0,b1},%5;\n"
+        "mul.wide.u32 p,a0,b0; mov.b64 {l0,h0},p;\n"
+        "mul.wide.u32 p,a0,b1; mov.b64 {l1,h1},p;\n"
+        "mul.wide.u32 p,a1,b0; mov.b64 {l2,h2},p;\n"
+        "mul.wide.u32 p,a1,b1; mov.b64 {l3,h3},p;\n"
+        "add.cc.u32 y1,h0,l1; addc.cc.u32 y2,l3,h1; addc.u32 y3,h3,0;\n"
+        "add.cc.u32 y1,y1,l2; addc.cc.u32 y2,y2,h2; addc.u32 y3,y3,0;\n"
+        "sub.cc.u32 %0,l0,y3; subc.cc.u32 %1,y1,0; subc.u32 %3,0,0;\n"      // (x1:x0) - x3, m = -borrow
+        "sub.cc.u32 %0,%0,%3; subc.u32 %1,%1,0;\n"                          // - EPS on borrow (x3 < 2^32: no second borrow)
+        "mov.u32 %2,y2; }"
+        : "=r"(r0), "=r"(r1), "=r"(x2), "=r"(m) : "l"(a), "l"(b));
+    (void)m;
     const u64 t1 = (u64)x2 * 0xFFFFFFFFu;      // < p, so the add below meets fadd_l's requirement
     return fadd_l(bmi_pack(r0, r1), t1);
 }
