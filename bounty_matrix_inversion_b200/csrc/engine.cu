@@ -29,11 +29,12 @@ struct bmi_ctx {
     bmi_params p;
     int device, logN;
     u64 ninv;
-    u64 *d_tw = nullptr, *d_twi = nullptr, *d_bsk = nullptr, *d_ksk = nullptr, *d_luts = nullptr;
+    u64 *d_tw = nullptr, *d_twi = nullptr, *d_ksk = nullptr, *d_luts = nullptr;
+    u64* d_bsk[2] = {nullptr, nullptr};   // transform-domain key in the layout of the throughput / latency build
     int n_luts = 0;
     int num_sms = 148;
     int64_t launches = 0;
-    int pbs_mode = 0;   // 0 auto (cluster kernel, build chosen per launch), 1 cluster kernel latency build, 2 single-CTA kernel
+    int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build
     // scratch for the host-buffer convenience path
     u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
     int *w_idx = nullptr, *w_lut = nullptr;
@@ -48,47 +49,50 @@ size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c-
 
 template <int L>
 int setup_attrs(const bmi_ctx* c) {
-    CK(cudaFuncSetAttribute(pbs_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    constexpr int TP = throughput_ctas_per_sm<L>();
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, TP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, TP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem(c)));
-    CK(cudaFuncSetAttribute(bsk_convert_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    CK(cudaFuncSetAttribute(polymul_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
+    const int sm = (int)pbs_smem(c);
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    CK(cudaFuncSetAttribute(polymul_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    CK(cudaFuncSetAttribute(polymul_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     return BMI_OK;
 }
 
+// both layouts of the transform-domain key: [0] throughput build (E = 4), [1] latency build
 template <int L>
-int launch_convert(bmi_ctx* c, const u64* src, u64* dst, int64_t polys, cudaStream_t st) {
-    bsk_convert_kernel<L><<<(unsigned)polys, NttCfg<L>::T, (1 << L) * 8, st>>>(src, dst, c->d_tw, c->ninv);
-    c->launches++;
+int launch_convert(bmi_ctx* c, const u64* src, int64_t p0, int64_t polys, cudaStream_t st) {
+    constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
+    const size_t off = (size_t)p0 * c->p.N;
+    bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, c->d_bsk[0] + off, c->d_tw, c->ninv);
+    bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, c->d_bsk[1] + off, c->d_tw, c->ninv);
+    c->launches += 2;
     CK(cudaGetLastError());
     return BMI_OK;
 }
 
 template <int L>
-int launch_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) {
+int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
+    constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
     const int64_t total = (int64_t)a.njobs * a.batch;
-    const unsigned grid = (unsigned)std::min<int64_t>(total, 1 << 20);
-    if (c->pbs_mode == 2) {
-        pbs_kernel<L><<<grid, NttCfg<L>::T, pbs_smem(c), st>>>(a);                   // one CTA per ciphertext
-    } else {
-        // CTA pair per ciphertext.  While the launch fits the resident CTA pairs of the all-in-registers build,
-        // latency wins; beyond one wave the higher-occupancy build does.
-        constexpr int TP = throughput_ctas_per_sm<L>();
-        const bool one = a.l == 1;
-        int resident = 1;
-        if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, 1, true>, NttCfg<L>::T, pbs_smem(c));
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, 1, false>, NttCfg<L>::T, pbs_smem(c));
-        const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
-        const bool latency = c->pbs_mode == 1 || total <= one_wave;
-        const dim3 g2(2 * grid), blk(NttCfg<L>::T);
-        if (latency && one) pbs_cluster_kernel<L, 1, true><<<g2, blk, pbs_smem(c), st>>>(a);
-        else if (latency) pbs_cluster_kernel<L, 1, false><<<g2, blk, pbs_smem(c), st>>>(a);
-        else if (one) pbs_cluster_kernel<L, TP, true><<<g2, blk, pbs_smem(c), st>>>(a);
-        else pbs_cluster_kernel<L, TP, false><<<g2, blk, pbs_smem(c), st>>>(a);
-    }
+    const unsigned grid = 2 * (unsigned)std::min<int64_t>(total, 1 << 20);      // one CTA pair per ciphertext
+    const bool one = a.l == 1;
+    // While the launch fits the CTA pairs the latency build keeps resident, latency wins; beyond one wave the
+    // 16-coefficients-per-thread build (fewer shared-memory round trips, more ciphertexts per SM) does.
+    int resident = 1;
+    if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true>, NttCfg<L, EL>::T, pbs_smem(c));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false>, NttCfg<L, EL>::T, pbs_smem(c));
+    const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
+    const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
+    a.bsk_hat = c->d_bsk[latency ? 1 : 0];
+    const size_t sm = pbs_smem(c);
+    if (latency && one) pbs_cluster_kernel<L, EL, 1, true><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
+    else if (latency) pbs_cluster_kernel<L, EL, 1, false><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
+    else if (one) pbs_cluster_kernel<L, ET, TP, true><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
+    else pbs_cluster_kernel<L, ET, TP, false><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
@@ -96,7 +100,9 @@ int launch_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) {
 
 template <int L>
 int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, cudaStream_t st) {
-    polymul_kernel<L><<<count, NttCfg<L>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
+    constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
+    if (c->pbs_mode == 1) polymul_kernel<L, EL><<<count, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
+    else polymul_kernel<L, ET><<<count, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
@@ -112,7 +118,7 @@ int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, 
     }
 
 int do_setup(bmi_ctx* c) { DISPATCH_L(c, setup_attrs<L>(c)); }
-int do_convert(bmi_ctx* c, const u64* s, u64* d, int64_t polys, cudaStream_t st) { DISPATCH_L(c, launch_convert<L>(c, s, d, polys, st)); }
+int do_convert(bmi_ctx* c, const u64* s, int64_t p0, int64_t polys, cudaStream_t st) { DISPATCH_L(c, launch_convert<L>(c, s, p0, polys, st)); }
 int do_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) { DISPATCH_L(c, launch_pbs<L>(c, a, st)); }
 int do_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* o, int n, cudaStream_t st) { DISPATCH_L(c, launch_polymul<L>(c, a, b, o, n, st)); }
 
@@ -173,7 +179,7 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
 int bmi_ctx_destroy(bmi_ctx* c) {
     if (!c) return BMI_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk); cudaFree(c->d_ksk); cudaFree(c->d_luts);
+    cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk[0]); cudaFree(c->d_bsk[1]); cudaFree(c->d_ksk); cudaFree(c->d_luts);
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
     cudaFree(c->ks_partial);
     delete c;
@@ -185,7 +191,8 @@ int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
     CK(cudaSetDevice(c->device));
     const int64_t polys = (int64_t)c->p.n * 2 * c->p.bsk_l * 2;
     const size_t bytes = (size_t)polys * c->p.N * 8;
-    if (!c->d_bsk) CK(cudaMalloc(&c->d_bsk, bytes));
+    for (int v = 0; v < 2; v++)
+        if (!c->d_bsk[v]) CK(cudaMalloc(&c->d_bsk[v], bytes));
     // upload in slices through a bounded staging buffer, converting slice by slice
     const int64_t slice = std::min<int64_t>(polys, 4096);
     u64* stage = nullptr;
@@ -193,7 +200,7 @@ int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
     for (int64_t p0 = 0; p0 < polys; p0 += slice) {
         const int64_t cnt = std::min(slice, polys - p0);
         CK(cudaMemcpy(stage, h_bsk + (size_t)p0 * c->p.N, (size_t)cnt * c->p.N * 8, cudaMemcpyHostToDevice));
-        int rc = do_convert(c, stage, c->d_bsk + (size_t)p0 * c->p.N, cnt, 0);
+        int rc = do_convert(c, stage, p0, cnt, 0);
         if (rc) { cudaFree(stage); return rc; }
         CK(cudaDeviceSynchronize());
     }
@@ -279,10 +286,10 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
 int bmi_pbs(bmi_ctx* c, const uint64_t* d_small, const int32_t* d_job_in, const int32_t* d_job_lut, const int32_t* d_job_out,
             uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
     if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
-    if (!c->d_bsk || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
+    if (!c->d_bsk[0] || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
     if (njobs == 0) return BMI_OK;
     PbsArgs a;
-    a.bsk_hat = c->d_bsk; a.tw = c->d_tw; a.twi = c->d_twi; a.luts = c->d_luts; a.small = d_small;
+    a.bsk_hat = nullptr; a.tw = c->d_tw; a.twi = c->d_twi; a.luts = c->d_luts; a.small = d_small;
     a.job_in = d_job_in; a.job_lut = d_job_lut; a.job_out = d_job_out; a.out = d_out;
     a.njobs = njobs; a.batch = batch; a.n = c->p.n; a.bl = c->p.bsk_bl; a.l = c->p.bsk_l;
     return do_pbs(c, a, (cudaStream_t)stream);

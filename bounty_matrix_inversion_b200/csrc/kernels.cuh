@@ -1,9 +1,9 @@
-// Device kernels of the TFHE hot path (sm_100a).  One CTA bootstraps one ciphertext.
+// Device kernels of the TFHE hot path (sm_100a).
 #pragma once
 #include "ntt.cuh"
 
 struct PbsArgs {
-    const u64* __restrict__ bsk_hat;   // [n][2l][2][16][T]  transform domain, x 1/N
+    const u64* __restrict__ bsk_hat;   // [n][2l][2][2^E][T]  transform domain, x 1/N, in the layout of the kernel's E
     const u64* __restrict__ tw;        // [N] psi^brv(i)
     const u64* __restrict__ twi;       // [N] psi^-brv(i)
     const u64* __restrict__ luts;      // [n_luts][N]
@@ -16,133 +16,75 @@ struct PbsArgs {
     int n, bl, l;
 };
 
-// ----------------------------------------------------------------------------
-// bootstrapping-key conversion: standard-domain polynomial -> kernel-native layout
+// The two builds of the bootstrap kernel per polynomial size: coefficients per thread (log2) and the CTAs per SM
+// the register budget is sized for.  Latency build: as many warps per transform as a CTA allows, all in registers.
+// Throughput build: the configuration that bootstraps the most ciphertexts per second with the GPU full
+// (measured, scripts/pbs_sweep.py).
 template <int L>
-__global__ void __launch_bounds__(NttCfg<L>::T) bsk_convert_kernel(const u64* __restrict__ src, u64* __restrict__ dst,
-                                                                   const u64* __restrict__ tw, u64 ninv) {
-    using C = NttCfg<L>;
+constexpr int latency_e() { return L <= 12 ? 2 : 3; }
+#ifndef BMI_TP_E11
+#define BMI_TP_E11 2
+#define BMI_TP_B11 2
+#define BMI_TP_E12 3
+#define BMI_TP_B12 2
+#define BMI_TP_E13 3
+#define BMI_TP_B13 1
+#endif
+template <int L>
+constexpr int throughput_e() { return L <= 11 ? BMI_TP_E11 : L == 12 ? BMI_TP_E12 : BMI_TP_E13; }
+template <int L>
+constexpr int throughput_ctas_per_sm() { return L <= 11 ? BMI_TP_B11 : L == 12 ? BMI_TP_B12 : BMI_TP_B13; }
+
+// ----------------------------------------------------------------------------
+// bootstrapping-key conversion: standard-domain polynomial -> transform domain in the layout of build E
+template <int L, int E>
+__global__ void __launch_bounds__(NttCfg<L, E>::T) bsk_convert_kernel(const u64* __restrict__ src, u64* __restrict__ dst,
+                                                                      const u64* __restrict__ tw, u64 ninv) {
+    using C = NttCfg<L, E>;
     extern __shared__ u64 smem[];
     const int tid = threadIdx.x;
     const u64* s = src + (size_t)blockIdx.x * C::N;
     u64* d = dst + (size_t)blockIdx.x * C::N;
-    u64 x[16];
+    u64 x[C::EPT];
 #pragma unroll
-    for (int q = 0; q < 16; q++) x[q] = s[q * C::T + tid];
-    ntt_forward<L>(x, smem, tw, tid);
+    for (int q = 0; q < C::EPT; q++) x[q] = s[q * C::T + tid];
+    ntt_forward<L, E>(x, smem, tw, tid);
 #pragma unroll
-    for (int q = 0; q < 16; q++) d[q * C::T + tid] = fmul_c(x[q], ninv);
+    for (int q = 0; q < C::EPT; q++) d[q * C::T + tid] = fmul_c(x[q], ninv);
 }
 
 // c = a * b mod (X^N + 1): exercises forward, pointwise and inverse transforms (self-test entry)
-template <int L>
-__global__ void __launch_bounds__(NttCfg<L>::T) polymul_kernel(const u64* __restrict__ a, const u64* __restrict__ b,
-                                                               u64* __restrict__ c, const u64* __restrict__ tw,
-                                                               const u64* __restrict__ twi, u64 ninv) {
-    using C = NttCfg<L>;
+template <int L, int E>
+__global__ void __launch_bounds__(NttCfg<L, E>::T) polymul_kernel(const u64* __restrict__ a, const u64* __restrict__ b,
+                                                                  u64* __restrict__ c, const u64* __restrict__ tw,
+                                                                  const u64* __restrict__ twi, u64 ninv) {
+    using C = NttCfg<L, E>;
     extern __shared__ u64 smem[];
     const int tid = threadIdx.x;
     const size_t off = (size_t)blockIdx.x * C::N;
-    u64 x[16], y[16];
+    u64 x[C::EPT], y[C::EPT];
 #pragma unroll
-    for (int q = 0; q < 16; q++) { x[q] = a[off + q * C::T + tid]; y[q] = b[off + q * C::T + tid]; }
-    ntt_forward<L>(x, smem, tw, tid);
-    ntt_forward<L>(y, smem, tw, tid);
+    for (int q = 0; q < C::EPT; q++) { x[q] = a[off + q * C::T + tid]; y[q] = b[off + q * C::T + tid]; }
+    ntt_forward<L, E>(x, smem, tw, tid);
+    ntt_forward<L, E>(y, smem, tw, tid);
 #pragma unroll
-    for (int q = 0; q < 16; q++) x[q] = fmul_l(fmul_l(x[q], y[q]), ninv);
-    ntt_inverse<L>(x, smem, twi, tid);
+    for (int q = 0; q < C::EPT; q++) x[q] = fmul_l(fmul_l(x[q], y[q]), ninv);
+    ntt_inverse<L, E>(x, smem, twi, tid);
 #pragma unroll
-    for (int q = 0; q < 16; q++) c[off + q * C::T + tid] = fcanon(x[q]);
+    for (int q = 0; q < C::EPT; q++) c[off + q * C::T + tid] = fcanon(x[q]);
 }
 
 // ----------------------------------------------------------------------------
-// programmable bootstrap: modulus switch -> blind rotation -> sample extraction
-template <int L>
-__global__ void __launch_bounds__(NttCfg<L>::T, 1) pbs_kernel(const PbsArgs a) {
-    using C = NttCfg<L>;
-    constexpr int N = C::N, T = C::T;
-    extern __shared__ u64 smem[];
-    u64* acc = smem;                  // [2][N]: mask polynomial, body polynomial
-    u64* buf = smem + 2 * N;          // [N] transform exchange buffer (swizzled)
-    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N);   // [n] switched mask
-    const int tid = threadIdx.x;
-    const int n = a.n, bl = a.bl, l = a.l, tot = bl * l;
-
-    for (int f = blockIdx.x; f < a.njobs * a.batch; f += gridDim.x) {
-        const int q0 = f / a.batch, b0 = f - q0 * a.batch;
-        const u64* in = a.small + ((size_t)a.job_in[q0] * a.batch + b0) * (n + 1);
-        const u64* lut = a.luts + (size_t)a.job_lut[q0] * N;
-        u64* out = a.out + ((size_t)a.job_out[q0] * a.batch + b0) * (N + 1);
-
-        __syncthreads();   // previous job fully written out
-        for (int i = tid; i < n; i += T) rot[i] = (unsigned short)modswitch(in[i], L);
-        {   // acc = (0, X^{-b~} * lut)
-            const u32 r0 = (2 * N - modswitch(in[n], L)) & (2 * N - 1);
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int idx = q * T + tid;
-                const u32 u = (idx + 2 * N - r0) & (2 * N - 1);
-                acc[idx] = 0;
-                acc[N + idx] = u < N ? lut[u] : fneg(lut[u - N]);
-            }
-        }
-        __syncthreads();
-
-        for (int i = 0; i < n; i++) {
-            const u32 at = rot[i];
-            if (at == 0) continue;   // X^0 - 1 = 0: nothing to add
-            u64 sum0[16], sum1[16];
-#pragma unroll
-            for (int q = 0; q < 16; q++) { sum0[q] = 0; sum1[q] = 0; }
-            const u64* g = a.bsk_hat + (size_t)i * (2 * l) * 2 * N;
-            for (int c = 0; c < 2; c++) {
-                const u64* A = acc + c * N;
-                for (int j = 1; j <= l; j++) {
-                    u64 x[16];
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {   // digit j of (X^at - 1) * acc_c
-                        const int idx = q * T + tid;
-                        const u32 u = (idx + 2 * N - at) & (2 * N - 1);
-                        const u64 r = u < N ? A[u] : fneg(A[u - N]);
-                        x[q] = digit_of(round_top(fsub(r, A[idx]), tot), bl, l, j);
-                    }
-                    ntt_forward<L>(x, buf, a.tw, tid);
-                    const u64* row = g + (size_t)(c * l + (j - 1)) * 2 * N;
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        sum0[q] = fadd_l(sum0[q], fmul_c(x[q], __ldg(row + q * T + tid)));
-                        sum1[q] = fadd_l(sum1[q], fmul_c(x[q], __ldg(row + N + q * T + tid)));
-                    }
-                }
-            }
-            ntt_inverse<L>(sum0, buf, a.twi, tid);
-            ntt_inverse<L>(sum1, buf, a.twi, tid);
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const int idx = q * T + tid;
-                acc[idx] = fcanon(fadd_l(sum0[q], acc[idx]));          // acc stays canonical in shared memory
-                acc[N + idx] = fcanon(fadd_l(sum1[q], acc[N + idx]));
-            }
-            __syncthreads();
-        }
-
-        // sample extraction of the constant coefficient
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int t = q * T + tid;
-            out[t] = t == 0 ? acc[0] : fneg(acc[N - t]);
-        }
-        if (tid == 0) out[N] = acc[N];
-    }
-}
-
-// ----------------------------------------------------------------------------
-// programmable bootstrap on a 2-CTA cluster: CTA c owns accumulator polynomial c (0 = mask, 1 = body).
-// Per CMUX each CTA decomposes and forward-transforms only ITS polynomial, multiplies it by both columns of
-// its GGSW rows, keeps the partial sum for its own output polynomial and pushes the partial sum for the
-// partner's polynomial straight into the partner's shared memory (DSMEM).  After the cluster barrier each CTA
-// adds what it received, inverse-transforms one polynomial and updates its accumulator: half the work and
-// half the registers of the single-CTA kernel per CTA, so one bootstrap finishes in about half the time.
+// programmable bootstrap (modulus switch -> blind rotation -> sample extraction) on a 2-CTA cluster:
+// CTA c owns accumulator polynomial c (0 = mask, 1 = body).  Per CMUX each CTA decomposes and forward-transforms
+// only ITS polynomial, multiplies it by both columns of its GGSW rows, keeps the partial sum for its own output
+// polynomial and pushes the partial sum for the partner's polynomial straight into the partner's shared memory
+// (DSMEM).  After the cluster barrier each CTA adds what it received, inverse-transforms one polynomial and
+// updates its accumulator.
+//   E         coefficients per thread (log2): 4 = throughput build, 2/3 = latency build (more warps per transform)
+//   MINB      CTAs per SM the register budget is sized for
+//   ONE_LEVEL l == 1 (every 128-bit parameter set this engine selects): the partner's partial sum is a single
+//             product per coefficient and goes straight to DSMEM instead of being accumulated in registers
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ u32 cluster_rank() { u32 r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -153,22 +95,15 @@ __device__ __forceinline__ u64* cluster_map(u64* p, u32 rank) {
     return reinterpret_cast<u64*>(out);
 }
 
-// MINB = CTAs per SM the register budget is sized for: 1 keeps everything in registers (lowest latency, used
-// while a launch fits one wave); throughput_ctas_per_sm<L>() trades a few spills for twice the resident warps.
-template <int L>
-constexpr int throughput_ctas_per_sm() { return L <= 11 ? 4 : L == 12 ? 2 : 1; }
-
-// ONE_LEVEL: l == 1 (every 128-bit parameter set this engine selects): the partner's partial sum is a single
-// product per coefficient and goes straight to DSMEM instead of being accumulated in 32 registers.
-template <int L, int MINB, bool ONE_LEVEL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
-    using C = NttCfg<L>;
-    constexpr int N = C::N, T = C::T;
+template <int L, int E, int MINB, bool ONE_LEVEL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
+    using C = NttCfg<L, E>;
+    constexpr int N = C::N, T = C::T, EPT = C::EPT;
     extern __shared__ u64 smem[];
-    u64* acc = smem;                  // [N] this CTA's accumulator polynomial
+    u64* acc = smem;                  // [N] this CTA's accumulator polynomial (canonical values)
     u64* buf = smem + N;              // [N] transform exchange buffer (swizzled)
     u64* recv = smem + 2 * N;         // [N] partial sums pushed by the partner CTA
-    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N);
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N);   // [n] switched mask
     const int tid = threadIdx.x;
     const u32 me = cluster_rank(), other = me ^ 1;
     u64* peer_recv = cluster_map(recv, other);
@@ -182,12 +117,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L>::T, MINB) 
         const u64* lut = a.luts + (size_t)a.job_lut[q0] * N;
         u64* out = a.out + ((size_t)a.job_out[q0] * a.batch + b0) * (N + 1);
 
-        __syncthreads();
+        __syncthreads();              // previous ciphertext fully written out
         for (int i = tid; i < n; i += T) rot[i] = (unsigned short)modswitch(in[i], L);
-        {
+        {   // acc = (0, X^{-b~} * lut)
             const u32 r0 = (2 * N - modswitch(in[n], L)) & (2 * N - 1);
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < EPT; q++) {
                 const int idx = q * T + tid;
                 const u32 u = (idx + 2 * N - r0) & (2 * N - 1);
                 acc[idx] = me == 0 ? 0 : (u < N ? lut[u] : fneg(lut[u - N]));
@@ -197,67 +132,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L>::T, MINB) 
 
         for (int i = 0; i < n; i++) {
             const u32 at = rot[i];
-            if (at == 0) continue;
-            u64 own[16];
+            if (at == 0) continue;    // X^0 - 1 = 0: nothing to add (same decision in both CTAs)
+            u64 own[EPT];
             const u64* g = a.bsk_hat + ((size_t)i * (2 * l) + me * l) * 2 * N;
             if (ONE_LEVEL) {
-                u64 x[16];
+                u64 x[EPT];
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
+                for (int q = 0; q < EPT; q++) {   // the digit of (X^at - 1) * acc
                     const int idx = q * T + tid;
                     const u32 u = (idx + 2 * N - at) & (2 * N - 1);
                     const u64 r = u < N ? acc[u] : fneg(acc[u - N]);
                     x[q] = digit_of(round_top(fsub(r, acc[idx]), tot), bl, 1, 1);
                 }
-                ntt_forward<L>(x, buf, a.tw, tid);
+                ntt_forward<L, E>(x, buf, a.tw, tid);
                 cluster_wait();       // partner has consumed what I pushed for the previous CMUX
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
+                for (int q = 0; q < EPT; q++) {
                     peer_recv[q * T + tid] = fmul_c(x[q], __ldg(g + other * N + q * T + tid));
                     own[q] = fmul_l(x[q], __ldg(g + me * N + q * T + tid));
                 }
             } else {
-                u64 oth[16];
+                u64 oth[EPT];
 #pragma unroll
-                for (int q = 0; q < 16; q++) { own[q] = 0; oth[q] = 0; }
+                for (int q = 0; q < EPT; q++) { own[q] = 0; oth[q] = 0; }
                 for (int j = 1; j <= l; j++) {
-                    u64 x[16];
+                    u64 x[EPT];
 #pragma unroll
-                    for (int q = 0; q < 16; q++) {
+                    for (int q = 0; q < EPT; q++) {
                         const int idx = q * T + tid;
                         const u32 u = (idx + 2 * N - at) & (2 * N - 1);
                         const u64 r = u < N ? acc[u] : fneg(acc[u - N]);
                         x[q] = digit_of(round_top(fsub(r, acc[idx]), tot), bl, l, j);
                     }
-                    ntt_forward<L>(x, buf, a.tw, tid);
+                    ntt_forward<L, E>(x, buf, a.tw, tid);
                     const u64* row = g + (size_t)(j - 1) * 2 * N;
 #pragma unroll
-                    for (int q = 0; q < 16; q++) {
+                    for (int q = 0; q < EPT; q++) {
                         own[q] = fadd_l(own[q], fmul_c(x[q], __ldg(row + me * N + q * T + tid)));
                         oth[q] = fadd_l(oth[q], fmul_c(x[q], __ldg(row + other * N + q * T + tid)));
                     }
                 }
                 cluster_wait();       // partner has consumed what I pushed for the previous CMUX
 #pragma unroll
-                for (int q = 0; q < 16; q++) peer_recv[q * T + tid] = fcanon(oth[q]);
+                for (int q = 0; q < EPT; q++) peer_recv[q * T + tid] = fcanon(oth[q]);
             }
             cluster_arrive();         // my push is visible ...
             cluster_wait();           // ... and so is the partner's
 #pragma unroll
-            for (int q = 0; q < 16; q++) own[q] = fadd_l(own[q], recv[q * T + tid]);
+            for (int q = 0; q < EPT; q++) own[q] = fadd_l(own[q], recv[q * T + tid]);
             cluster_arrive();         // recv may be overwritten again
-            ntt_inverse<L>(own, buf, a.twi, tid);
+            ntt_inverse<L, E>(own, buf, a.twi, tid);
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < EPT; q++) {
                 const int idx = q * T + tid;
                 acc[idx] = fcanon(fadd_l(own[q], acc[idx]));
             }
             __syncthreads();
         }
 
+        // sample extraction of the constant coefficient
         if (me == 0) {
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < EPT; q++) {
                 const int t = q * T + tid;
                 out[t] = t == 0 ? acc[0] : fneg(acc[N - t]);
             }

@@ -156,7 +156,7 @@ class Engine:
         self.n_luts = luts.shape[0]
 
     def set_pbs_mode(self, mode: int):
-        """0 automatic, 1 always the 2-CTA cluster kernel, 2 always the single-CTA kernel"""
+        """bootstrap kernel build: 0 automatic per launch size, 1 latency build, 2 throughput build"""
         _check(lib().bmi_ctx_set_pbs_mode(self._h, mode))
 
     @property

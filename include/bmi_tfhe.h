@@ -68,8 +68,8 @@ int bmi_ctx_load_bsk(bmi_ctx* ctx, const uint64_t* h_bsk);   /* upload + convert
 int bmi_ctx_load_ksk(bmi_ctx* ctx, const uint64_t* h_ksk);
 int bmi_ctx_load_luts(bmi_ctx* ctx, const uint64_t* h_luts, int32_t n_luts);   /* [n_luts][N] accumulator polynomials */
 int64_t bmi_ctx_launch_count(const bmi_ctx* ctx);            /* kernels launched by this context so far */
-/* bootstrap kernel choice: 0 = automatic (CTA pair per ciphertext; register budget picked per launch size),
- * 1 = CTA pair, all-in-registers build (lowest latency), 2 = one CTA per ciphertext */
+/* bootstrap kernel build: 0 = automatic (picked per launch size), 1 = latency build (4 or 8 coefficients per thread:
+ * most warps per transform), 2 = throughput build (16 coefficients per thread); bmi_polymul_host follows the same choice */
 int bmi_ctx_set_pbs_mode(bmi_ctx* ctx, int32_t mode);
 
 /* out[j][b] = sum_t coef[t] * vals[idx[t]][b] + konst[j], rows of k*N+1 words.

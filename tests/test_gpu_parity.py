@@ -33,8 +33,10 @@ def setup(request, native, oracle):
     eng.close()
 
 
-def test_polymul_matches_oracle(setup, oracle):
+@pytest.mark.parametrize("mode", [1, 2], ids=["latency_build", "throughput_build"])
+def test_polymul_matches_oracle(setup, oracle, mode):
     prm, _, eng = setup
+    eng.set_pbs_mode(mode)
     rng = np.random.default_rng(prm.N)
     a, b = rand_field(rng, (3, prm.N)), rand_field(rng, (3, prm.N))
     a[2] = 0; a[2, 1] = 1; b[2] = 0; b[2, prm.N - 1] = 1          # X * X^(N-1) = -1
@@ -42,6 +44,7 @@ def test_polymul_matches_oracle(setup, oracle):
     for i in range(3):
         assert np.array_equal(got[i], oracle.negacyclic_mul(a[i], b[i]))
     assert got[2, 0] == P - 1 and not got[2, 1:].any()
+    eng.set_pbs_mode(0)
 
 
 def test_keyswitch_matches_oracle(setup, oracle):
@@ -59,7 +62,7 @@ def test_keyswitch_matches_oracle(setup, oracle):
         assert np.array_equal(got[i], oracle.keyswitch(prm, keys.ksk, big[i])), i
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["cluster2", "single"])
+@pytest.mark.parametrize("mode", [1, 2], ids=["latency_build", "throughput_build"])
 def test_pbs_matches_oracle_bit_exact(setup, oracle, mode):
     prm, keys, eng = setup
     eng.set_pbs_mode(mode)
