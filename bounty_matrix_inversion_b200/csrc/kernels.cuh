@@ -20,8 +20,12 @@ struct PbsArgs {
 // the register budget is sized for.  Latency build: as many warps per transform as a CTA allows, all in registers.
 // Throughput build: the configuration that bootstraps the most ciphertexts per second with the GPU full
 // (measured, scripts/pbs_sweep.py).
+#ifndef BMI_LAT_E11
+#define BMI_LAT_E11 2
+#define BMI_LAT_E12 3
+#endif
 template <int L>
-constexpr int latency_e() { return L <= 12 ? 2 : 3; }
+constexpr int latency_e() { return L <= 11 ? BMI_LAT_E11 : L == 12 ? BMI_LAT_E12 : 3; }
 #ifndef BMI_TP_E11
 #define BMI_TP_E11 2
 #define BMI_TP_B11 2
