@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,6 +35,7 @@ struct bmi_ctx {
     int n_luts = 0;
     int num_sms = 148;
     int64_t launches = 0;
+    bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
     int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build
     // scratch for the host-buffer convenience path
     u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
@@ -45,16 +47,22 @@ struct bmi_ctx {
 
 namespace {
 
+constexpr int kMaxSmem = 227 * 1024;   // dynamic shared memory a CTA can opt into on sm_100
+
 size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
+
+size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
 
 template <int L>
 int setup_attrs(const bmi_ctx* c) {
     constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
-    const int sm = (int)pbs_smem(c);
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    const int sm = (int)pbs_smem(c), sms = (int)pbs_smem_staged(c);
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+    if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
+    if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
     CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(polymul_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
@@ -83,16 +91,20 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     // While the launch fits the CTA pairs the latency build keeps resident, latency wins; beyond one wave the
     // 16-coefficients-per-thread build (fewer shared-memory round trips, more ciphertexts per SM) does.
     int resident = 1;
-    if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true>, NttCfg<L, EL>::T, pbs_smem(c));
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false>, NttCfg<L, EL>::T, pbs_smem(c));
+    if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true, false>, NttCfg<L, EL>::T, pbs_smem(c));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
     const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
     const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
     a.bsk_hat = c->d_bsk[latency ? 1 : 0];
-    const size_t sm = pbs_smem(c);
-    if (latency && one) pbs_cluster_kernel<L, EL, 1, true><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
-    else if (latency) pbs_cluster_kernel<L, EL, 1, false><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
-    else if (one) pbs_cluster_kernel<L, ET, TP, true><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
-    else pbs_cluster_kernel<L, ET, TP, false><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
+    const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
+    // GGSW rows staged by TMA whenever the extra 2N words still leave room for the CTAs per SM the build is sized for
+    const bool stage = one && c->tma_stage && (latency ? (int)sms <= kMaxSmem : (int)sms * TP <= kMaxSmem);
+    if (latency && stage) pbs_cluster_kernel<L, EL, 1, true, true><<<grid, NttCfg<L, EL>::T, sms, st>>>(a);
+    else if (latency && one) pbs_cluster_kernel<L, EL, 1, true, false><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
+    else if (latency) pbs_cluster_kernel<L, EL, 1, false, false><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
+    else if (stage) pbs_cluster_kernel<L, ET, TP, true, true><<<grid, NttCfg<L, ET>::T, sms, st>>>(a);
+    else if (one) pbs_cluster_kernel<L, ET, TP, true, false><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
+    else pbs_cluster_kernel<L, ET, TP, false, false><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
@@ -170,6 +182,7 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     CK(cudaMalloc(&c->d_twi, p->N * 8));
     CK(cudaMemcpy(c->d_tw, tw.data(), p->N * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_twi, twi.data(), p->N * 8, cudaMemcpyHostToDevice));
+    if (const char* v = getenv("BMI_TMA_STAGE")) c->tma_stage = v[0] == '1';
     int rc = do_setup(c);
     if (rc) { delete c; return rc; }
     *out = c;
@@ -229,6 +242,12 @@ int bmi_ctx_load_luts(bmi_ctx* c, const uint64_t* h_luts, int32_t n_luts) {
 }
 
 int64_t bmi_ctx_launch_count(const bmi_ctx* c) { return c ? c->launches : 0; }
+
+int bmi_ctx_set_tma_stage(bmi_ctx* c, int32_t on) {
+    if (!c) { set_error("invalid argument"); return BMI_EINVAL; }
+    c->tma_stage = on != 0;
+    return BMI_OK;
+}
 
 int bmi_ctx_set_pbs_mode(bmi_ctx* c, int32_t mode) {
     if (!c || mode < 0 || mode > 2) { set_error("invalid argument"); return BMI_EINVAL; }

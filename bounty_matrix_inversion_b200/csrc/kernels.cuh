@@ -99,7 +99,26 @@ __device__ __forceinline__ u64* cluster_map(u64* p, u32 rank) {
     return reinterpret_cast<u64*>(out);
 }
 
-template <int L, int E, int MINB, bool ONE_LEVEL>
+// ---- TMA bulk copy global -> shared with mbarrier completion (SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile("{ .reg .pred p;\n"
+                 "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra D;\n bra W;\n D: }" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+//   STAGE     (ONE_LEVEL only) the two GGSW row polynomials of the next CMUX are brought into shared memory by one
+//             TMA bulk copy issued a whole CMUX ahead, instead of per-thread global loads after the transform
+template <int L, int E, int MINB, bool ONE_LEVEL, bool STAGE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
     using C = NttCfg<L, E>;
     constexpr int N = C::N, T = C::T, EPT = C::EPT;
@@ -107,12 +126,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
     u64* acc = smem;                  // [N] this CTA's accumulator polynomial (canonical values)
     u64* buf = smem + N;              // [N] transform exchange buffer (swizzled)
     u64* recv = smem + 2 * N;         // [N] partial sums pushed by the partner CTA
-    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N);   // [n] switched mask
+    u64* stage = smem + 3 * N;        // [2N] GGSW rows of the coming CMUX (STAGE only)
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + (STAGE ? 5 : 3) * N);   // [n] switched mask
+    __shared__ __align__(8) u64 stage_bar;
     const int tid = threadIdx.x;
     const u32 me = cluster_rank(), other = me ^ 1;
     u64* peer_recv = cluster_map(recv, other);
     const int n = a.n, bl = a.bl, l = a.l, tot = bl * l;
     const int total = a.njobs * a.batch;
+    u32 stage_phase = 0;
+    if (STAGE) {
+        if (tid == 0) mbar_init(&stage_bar, 1);
+        __syncthreads();
+    }
+    // thread 0: start the bulk copy of the rows of the first CMUX at or after `from` that is not skipped
+    auto prefetch_rows = [&](int from) {
+        for (int i = from; i < n; i++)
+            if (rot[i] != 0) {
+                tma_load_1d(stage, a.bsk_hat + ((size_t)i * 2 + me) * 2 * N, 2 * N * 8, &stage_bar);
+                return;
+            }
+    };
 
     cluster_arrive();                 // opens the "recv is free" barrier of the first CMUX
     for (int f = blockIdx.x >> 1; f < total; f += gridDim.x >> 1) {
@@ -133,6 +167,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
             }
         }
         __syncthreads();
+        if (STAGE && tid == 0) prefetch_rows(0);
 
         for (int i = 0; i < n; i++) {
             const u32 at = rot[i];
@@ -150,10 +185,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
                 }
                 ntt_forward<L, E>(x, buf, a.tw, tid);
                 cluster_wait();       // partner has consumed what I pushed for the previous CMUX
+                if (STAGE) {
+                    mbar_wait(&stage_bar, stage_phase);
+                    stage_phase ^= 1;
 #pragma unroll
-                for (int q = 0; q < EPT; q++) {
-                    peer_recv[q * T + tid] = fmul_c(x[q], __ldg(g + other * N + q * T + tid));
-                    own[q] = fmul_l(x[q], __ldg(g + me * N + q * T + tid));
+                    for (int q = 0; q < EPT; q++) {
+                        peer_recv[q * T + tid] = fmul_c(x[q], stage[other * N + q * T + tid]);
+                        own[q] = fmul_l(x[q], stage[me * N + q * T + tid]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < EPT; q++) {
+                        peer_recv[q * T + tid] = fmul_c(x[q], __ldg(g + other * N + q * T + tid));
+                        own[q] = fmul_l(x[q], __ldg(g + me * N + q * T + tid));
+                    }
                 }
             } else {
                 u64 oth[EPT];
@@ -181,7 +226,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
                 for (int q = 0; q < EPT; q++) peer_recv[q * T + tid] = fcanon(oth[q]);
             }
             cluster_arrive();         // my push is visible ...
-            cluster_wait();           // ... and so is the partner's
+            cluster_wait();           // ... and so is the partner's; every thread of this CTA is past its reads of `stage`
+            if (STAGE && tid == 0) prefetch_rows(i + 1);
 #pragma unroll
             for (int q = 0; q < EPT; q++) own[q] = fadd_l(own[q], recv[q * T + tid]);
             cluster_arrive();         // recv may be overwritten again

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "bmi_ctx_load_luts": (C.c_int, [C.c_void_p, U64P, C.c_int32]),
     "bmi_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "bmi_ctx_set_pbs_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bmi_ctx_set_tma_stage": (C.c_int, [C.c_void_p, C.c_int32]),
     "bmi_lincomb": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_void_p]),
     "bmi_keyswitch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bmi_pbs": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p]),
@@ -158,6 +159,10 @@ class Engine:
     def set_pbs_mode(self, mode: int):
         """bootstrap kernel build: 0 automatic per launch size, 1 latency build, 2 throughput build"""
         _check(lib().bmi_ctx_set_pbs_mode(self._h, mode))
+
+    def set_tma_stage(self, on: bool):
+        """GGSW rows through TMA bulk copies into shared memory (off by default: measured slower than direct loads)"""
+        _check(lib().bmi_ctx_set_tma_stage(self._h, int(bool(on))))
 
     @property
     def launch_count(self) -> int:

@@ -90,6 +90,32 @@ def test_pbs_matches_oracle_bit_exact(setup, oracle, mode):
     eng.set_pbs_mode(0)
 
 
+def test_pbs_tma_staged_rows_match_oracle(setup, oracle):
+    """the TMA-staged variant of the bootstrap (bmi_ctx_set_tma_stage) is bit-identical too"""
+    prm, keys, eng = setup
+    if prm.bsk_l != 1:
+        pytest.skip("row staging is built for one decomposition level")
+    luts = np.stack([PR.lut_polynomial([PR.encode(t, 3) for t in (3, 1, 4, 1, 5, 9, 2, 6)], 3, prm.N)])
+    eng.load_luts(luts)
+    cts = keys.encrypt([PR.encode(m, 3) for m in range(5)])
+    small = np.stack([oracle.keyswitch(prm, keys.ksk, c) for c in cts])
+    import torch
+    idx = torch.arange(5, dtype=torch.int32, device="cuda")
+    lut = torch.zeros(5, dtype=torch.int32, device="cuda")
+    eng.set_tma_stage(True)
+    try:
+        for mode in (1, 2):
+            eng.set_pbs_mode(mode)
+            out = torch.zeros((5, prm.big_dim + 1), dtype=torch.int64, device="cuda")
+            eng.pbs(dev(small), idx, lut, idx, out, 5)
+            got = host_u64(out)
+            for i in range(5):
+                assert np.array_equal(got[i], oracle.pbs(prm, keys.bsk, luts[0], small[i])), (mode, i)
+    finally:
+        eng.set_tma_stage(False)
+        eng.set_pbs_mode(0)
+
+
 def test_pbs_batch_lanes(setup, oracle):
     """batch > 1: job q lane b reads row job_in[q]*batch+b and writes row job_out[q]*batch+b"""
     prm, keys, eng = setup
