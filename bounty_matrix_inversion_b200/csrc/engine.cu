@@ -9,7 +9,7 @@
 
 #include "../../include/bmi_tfhe.h"
 #include "host_common.h"
-#include "kernels.cuh"
+#include "split.cuh"
 
 namespace bmi_host {
 static thread_local std::string g_err;
@@ -31,12 +31,13 @@ struct bmi_ctx {
     int device, logN;
     u64 ninv;
     u64 *d_tw = nullptr, *d_twi = nullptr, *d_ksk = nullptr, *d_luts = nullptr;
-    u64* d_bsk[2] = {nullptr, nullptr};   // transform-domain key in the layout of the throughput / latency build
+    u64* d_bsk[3] = {nullptr, nullptr, nullptr};   // transform-domain key: throughput build / latency build / 8-CTA split kernel
     int n_luts = 0;
     int num_sms = 148;
     int64_t launches = 0;
+    int split_clusters = -1;   // resident 8-CTA clusters of the split kernel (queried once)
     bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
-    int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build
+    int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel
     // scratch for the host-buffer convenience path
     u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
     int *w_idx = nullptr, *w_lut = nullptr;
@@ -51,6 +52,7 @@ constexpr int kMaxSmem = 227 * 1024;   // dynamic shared memory a CTA can opt in
 
 size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
 
+size_t split_smem(const bmi_ctx* c) { return (size_t)5 * (c->p.N / 4) * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
 size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
 
 template <int L>
@@ -63,6 +65,8 @@ int setup_attrs(const bmi_ctx* c) {
     CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
     if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
     if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
+    CK(cudaFuncSetAttribute(pbs_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
+    CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, (L <= 12 ? 2 : 3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     CK(cudaFuncSetAttribute(polymul_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
@@ -77,9 +81,31 @@ int launch_convert(bmi_ctx* c, const u64* src, int64_t p0, int64_t polys, cudaSt
     const size_t off = (size_t)p0 * c->p.N;
     bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, c->d_bsk[0] + off, c->d_tw, c->ninv);
     bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, c->d_bsk[1] + off, c->d_tw, c->ninv);
-    c->launches += 2;
+    constexpr int EC = L <= 12 ? 2 : 3;
+    bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, c->d_bsk[2] + off, c->d_tw, c->ninv);
+    c->launches += 3;
     CK(cudaGetLastError());
     return BMI_OK;
+}
+
+// how many 8-CTA clusters of the split kernel the GPU keeps resident at once (cluster placement is per GPC)
+template <int L>
+int64_t split_capacity(bmi_ctx* c) {
+    if (c->split_clusters < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8 * 64);
+        cfg.blockDim = dim3(SplitCfg<L>::T);
+        cfg.dynamicSmemBytes = split_smem(c);
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 8; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, pbs_split_kernel<L>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = c->num_sms / 10; }
+        c->split_clusters = n;
+    }
+    return c->split_clusters;
 }
 
 template <int L>
@@ -94,6 +120,14 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true, false>, NttCfg<L, EL>::T, pbs_smem(c));
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
     const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
+    // A handful of ciphertexts: spread each over an 8-CTA cluster (4 CTAs per polynomial), lowest latency.
+    if (one && (c->pbs_mode == 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) {
+        a.bsk_hat = c->d_bsk[2];
+        pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
+        c->launches++;
+        CK(cudaGetLastError());
+        return BMI_OK;
+    }
     const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
     a.bsk_hat = c->d_bsk[latency ? 1 : 0];
     const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
@@ -113,6 +147,12 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
 template <int L>
 int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, cudaStream_t st) {
     constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
+    if (c->pbs_mode == 3) {
+        polymul_split_kernel<L><<<4 * count, SplitCfg<L>::T, 3 * SplitCfg<L>::M * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
+        c->launches++;
+        CK(cudaGetLastError());
+        return BMI_OK;
+    }
     if (c->pbs_mode == 1) polymul_kernel<L, EL><<<count, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
     else polymul_kernel<L, ET><<<count, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
     c->launches++;
@@ -192,7 +232,7 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
 int bmi_ctx_destroy(bmi_ctx* c) {
     if (!c) return BMI_OK;
     cudaSetDevice(c->device);
-    cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk[0]); cudaFree(c->d_bsk[1]); cudaFree(c->d_ksk); cudaFree(c->d_luts);
+    cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk[0]); cudaFree(c->d_bsk[1]); cudaFree(c->d_bsk[2]); cudaFree(c->d_ksk); cudaFree(c->d_luts);
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
     cudaFree(c->ks_partial);
     delete c;
@@ -204,7 +244,7 @@ int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
     CK(cudaSetDevice(c->device));
     const int64_t polys = (int64_t)c->p.n * 2 * c->p.bsk_l * 2;
     const size_t bytes = (size_t)polys * c->p.N * 8;
-    for (int v = 0; v < 2; v++)
+    for (int v = 0; v < 3; v++)
         if (!c->d_bsk[v]) CK(cudaMalloc(&c->d_bsk[v], bytes));
     // upload in slices through a bounded staging buffer, converting slice by slice
     const int64_t slice = std::min<int64_t>(polys, 4096);
@@ -250,7 +290,7 @@ int bmi_ctx_set_tma_stage(bmi_ctx* c, int32_t on) {
 }
 
 int bmi_ctx_set_pbs_mode(bmi_ctx* c, int32_t mode) {
-    if (!c || mode < 0 || mode > 2) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (!c || mode < 0 || mode > 3) { set_error("invalid argument"); return BMI_EINVAL; }
     c->pbs_mode = mode;
     return BMI_OK;
 }

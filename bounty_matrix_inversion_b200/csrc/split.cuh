@@ -1,0 +1,214 @@
+// Bootstrap on an 8-CTA cluster: each of the two accumulator polynomials is spread over S = 4 CTAs (CTA r of a
+// group holds the coefficients i = r mod 4), so one ciphertext uses 8 SMs and each CTA transforms only N/4 points.
+//
+// Distributed negacyclic NTT of size N = 2^L over the 4 CTAs of a group (M = N/4 points, T = M/4 threads each):
+//   forward : the first L-2 Cooley-Tukey stages pair positions that are congruent mod 4, i.e. they are a size-M
+//             transform local to each CTA (the twiddles tw[1..M) of the size-N table ARE the size-M table);
+//             one all-to-all over DSMEM then hands every CTA complete blocks of 4 consecutive positions, on which
+//             the last two stages run in registers (one block per thread).
+//   inverse : the mirror image (two Gentleman-Sande stages on blocks, all-to-all back, local size-M inverse).
+// After the forward transform CTA r holds positions [r*M, (r+1)*M); thread t holds (r*T + t)*4 + e, e = 0..3.
+#pragma once
+#include "kernels.cuh"
+
+constexpr int kSplit = 4;        // CTAs per polynomial
+constexpr int kSplitE = 2;       // coefficients per thread (log2) == log2(kSplit): one block per thread
+
+template <int L>
+struct SplitCfg {
+    static constexpr int LL = L - 2;             // local transform size (log2)
+    static constexpr int N = 1 << L, M = N / 4, T = M / 4;
+    using Local = NttCfg<L - 2, kSplitE>;
+};
+
+__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
+
+// x: 4 registers in pass-0 layout of the local transform (slot q <-> local coefficient q*T + tid <-> global
+// coefficient (q*T + tid)*4 + r).  Out: y[e] = transform value at position (r*T + tid)*4 + e.
+// gbuf: [M] words in every CTA of the group; group0 = cluster rank of the group's CTA 0.
+template <int L>
+__device__ __forceinline__ void split_forward(u64 (&x)[4], u64* buf, u64* gbuf, const u64* __restrict__ tw, int tid,
+                                              u32 group0, u32 r) {
+    using C = SplitCfg<L>;
+    using LC = typename C::Local;
+    ntt_forward<C::LL, kSplitE>(x, buf, tw, tid);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {     // all-to-all: local position jl goes to the CTA that owns block jl
+        const int jl = slot_index<C::LL, kSplitE>(LC::NPASS - 1, q, tid);
+        const u32 dst = (u32)(jl >> (C::LL - 2));
+        const int b = jl & (C::T - 1);
+        cluster_map(gbuf, group0 + dst)[b * 4 + (int)r] = x[q];
+    }
+    cluster_sync_all();
+    const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(gbuf + tid * 4);
+    const ulonglong2 v23 = *reinterpret_cast<const ulonglong2*>(gbuf + tid * 4 + 2);
+    x[0] = v01.x; x[1] = v01.y; x[2] = v23.x; x[3] = v23.y;
+    const int blk = (int)r * C::T + tid;
+    const u64 wa = __ldg(tw + (1 << (L - 2)) + blk);
+    butterfly<false>(x[0], x[2], wa);
+    butterfly<false>(x[1], x[3], wa);
+    butterfly<false>(x[0], x[1], __ldg(tw + (1 << (L - 1)) + 2 * blk));
+    butterfly<false>(x[2], x[3], __ldg(tw + (1 << (L - 1)) + 2 * blk + 1));
+}
+
+// in: z[e] at position (r*T + tid)*4 + e.  Out: 4 registers in pass-0 layout of the local transform, times N.
+// lbuf: [M] words in every CTA of the group.
+template <int L>
+__device__ __forceinline__ void split_inverse(u64 (&z)[4], u64* buf, u64* lbuf, const u64* __restrict__ twi, int tid,
+                                              u32 group0, u32 r) {
+    using C = SplitCfg<L>;
+    using LC = typename C::Local;
+    const int blk = (int)r * C::T + tid;
+    butterfly<true>(z[0], z[1], __ldg(twi + (1 << (L - 1)) + 2 * blk));
+    butterfly<true>(z[2], z[3], __ldg(twi + (1 << (L - 1)) + 2 * blk + 1));
+    const u64 wa = __ldg(twi + (1 << (L - 2)) + blk);
+    butterfly<true>(z[0], z[2], wa);
+    butterfly<true>(z[1], z[3], wa);
+#pragma unroll
+    for (int e = 0; e < 4; e++) cluster_map(lbuf, group0 + e)[blk] = z[e];   // position blk*4+e lives in CTA e, local blk
+    cluster_sync_all();
+#pragma unroll
+    for (int q = 0; q < 4; q++) z[q] = lbuf[slot_index<C::LL, kSplitE>(LC::NPASS - 1, q, tid)];
+    ntt_inverse<C::LL, kSplitE>(z, buf, twi, tid);
+}
+
+// self-test: c = a * b mod (X^N + 1) for one polynomial pair per 4-CTA cluster
+template <int L>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SplitCfg<L>::T) polymul_split_kernel(
+    const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ c, const u64* __restrict__ tw,
+    const u64* __restrict__ twi, u64 ninv) {
+    using C = SplitCfg<L>;
+    extern __shared__ u64 smem[];
+    u64 *buf = smem, *gbuf = smem + C::M, *lbuf = smem + 2 * C::M;
+    const int tid = threadIdx.x;
+    const u32 r = cluster_rank();
+    const size_t off = (size_t)(blockIdx.x / 4) * C::N;
+    u64 x[4], y[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int gi = (q * C::T + tid) * 4 + (int)r;
+        x[q] = a[off + gi];
+        y[q] = b[off + gi];
+    }
+    split_forward<L>(x, buf, gbuf, tw, tid, 0, r);
+    cluster_sync_all();               // gbuf is reused by the second transform
+    split_forward<L>(y, buf, gbuf, tw, tid, 0, r);
+#pragma unroll
+    for (int e = 0; e < 4; e++) x[e] = fmul_l(fmul_l(x[e], y[e]), ninv);
+    split_inverse<L>(x, buf, lbuf, twi, tid, 0, r);
+#pragma unroll
+    for (int q = 0; q < 4; q++) c[off + (q * C::T + tid) * 4 + (int)r] = fcanon(x[q]);
+}
+
+// ----------------------------------------------------------------------------
+// key conversion for the split layout: [poly][r][e][t] <- transform value at position (r*T + t)*4 + e
+template <int L, int E>
+__global__ void __launch_bounds__(NttCfg<L, E>::T) bsk_convert_split_kernel(const u64* __restrict__ src, u64* __restrict__ dst,
+                                                                            const u64* __restrict__ tw, u64 ninv) {
+    using C = NttCfg<L, E>;
+    using S = SplitCfg<L>;
+    extern __shared__ u64 smem[];
+    const int tid = threadIdx.x;
+    const u64* s = src + (size_t)blockIdx.x * C::N;
+    u64* d = dst + (size_t)blockIdx.x * C::N;
+    u64 x[C::EPT];
+#pragma unroll
+    for (int q = 0; q < C::EPT; q++) x[q] = s[q * C::T + tid];
+    ntt_forward<L, E>(x, smem, tw, tid);
+#pragma unroll
+    for (int q = 0; q < C::EPT; q++) {
+        const int P = slot_index<L, E>(C::NPASS - 1, q, tid);
+        const int blk = P >> 2, e = P & 3;
+        d[(blk / S::T) * S::M + e * S::T + (blk % S::T)] = fmul_c(x[q], ninv);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// programmable bootstrap, one 8-CTA cluster per ciphertext (l == 1, k == 1).  Cluster rank = c*4 + r:
+// c = accumulator polynomial (0 mask, 1 body), r = coefficient residue mod 4 held by the CTA.
+template <int L>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) pbs_split_kernel(const PbsArgs a) {
+    using C = SplitCfg<L>;
+    constexpr int N = C::N, M = C::M, T = C::T;
+    extern __shared__ u64 smem[];
+    u64* acc = smem;                  // [M] coefficients i = r mod 4 of polynomial c, local index i / 4 (canonical)
+    u64* buf = smem + M;              // [M] local transform exchange buffer
+    u64* gbuf = smem + 2 * M;         // [M] forward all-to-all landing zone
+    u64* lbuf = smem + 3 * M;         // [M] inverse all-to-all landing zone
+    u64* recv = smem + 4 * M;         // [M] partial sums from the partner polynomial's CTA
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 5 * M);
+    const int tid = threadIdx.x;
+    const u32 rank = cluster_rank(), c = rank >> 2, r = rank & 3, group0 = c << 2;
+    u64* peer_recv = cluster_map(recv, ((c ^ 1) << 2) + r);
+    const int n = a.n, bl = a.bl;
+    const int total = a.njobs * a.batch;
+
+    for (int f = blockIdx.x >> 3; f < total; f += gridDim.x >> 3) {
+        const int q0 = f / a.batch, b0 = f - q0 * a.batch;
+        const u64* in = a.small + ((size_t)a.job_in[q0] * a.batch + b0) * (n + 1);
+        const u64* lut = a.luts + (size_t)a.job_lut[q0] * N;
+        u64* out = a.out + ((size_t)a.job_out[q0] * a.batch + b0) * (N + 1);
+
+        cluster_sync_all();           // every CTA is done with the previous ciphertext's accumulator
+        for (int i = tid; i < n; i += T) rot[i] = (unsigned short)modswitch(in[i], L);
+        {   // acc = (0, X^{-b~} * lut), this CTA's residue class
+            const u32 r0 = (2 * N - modswitch(in[n], L)) & (2 * N - 1);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lc = q * T + tid, gi = lc * 4 + (int)r;
+                const u32 u = (gi + 2 * N - r0) & (2 * N - 1);
+                acc[lc] = c == 0 ? 0 : (u < N ? lut[u] : fneg(lut[u - N]));
+            }
+        }
+        __syncthreads();
+
+        for (int i = 0; i < n; i++) {
+            const u32 at = rot[i];
+            if (at == 0) continue;    // same decision in all 8 CTAs
+            cluster_sync_all();       // accumulator updates of the previous CMUX are visible cluster-wide
+            u64 x[4];
+            {   // digit of (X^at - 1) * acc: the rotated coefficients of this residue class all live in ONE CTA of the group
+                const u64* src = cluster_map(acc, group0 + ((r - at) & 3));
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int lc = q * T + tid, gi = lc * 4 + (int)r;
+                    const u32 u = (gi + 2 * N - at) & (2 * N - 1);
+                    const u64 v = src[(u & (N - 1)) >> 2];
+                    const u64 rv = u < N ? v : fneg(v);
+                    x[q] = digit_of(round_top(fsub(rv, acc[lc]), bl), bl, 1, 1);
+                }
+            }
+            split_forward<L>(x, buf, gbuf, a.tw, tid, group0, r);
+            const u64* g = a.bsk_hat + ((size_t)i * 2 + c) * 2 * N + (size_t)r * M;
+            u64 own[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                peer_recv[e * T + tid] = fmul_c(x[e], __ldg(g + (size_t)(c ^ 1) * N + e * T + tid));
+                own[e] = fmul_l(x[e], __ldg(g + (size_t)c * N + e * T + tid));
+            }
+            cluster_sync_all();
+#pragma unroll
+            for (int e = 0; e < 4; e++) own[e] = fadd_l(own[e], recv[e * T + tid]);
+            split_inverse<L>(own, buf, lbuf, a.twi, tid, group0, r);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lc = q * T + tid;
+                acc[lc] = fcanon(fadd_l(own[q], acc[lc]));
+            }
+        }
+
+        cluster_sync_all();
+        // sample extraction: out[0] = A[0], out[t] = -A[N - t]; coefficient N - t is held by residue (-t) mod 4
+        if (c == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lc = q * T + tid, gi = lc * 4 + (int)r;      // this CTA's coefficient gi goes to out[(N - gi) % N]
+                const u64 v = acc[lc];
+                if (gi == 0) out[0] = v; else out[N - gi] = fneg(v);
+            }
+        } else if (r == 0 && tid == 0) {
+            out[N] = acc[0];
+        }
+    }
+    cluster_sync_all();               // nobody exits while its shared memory may still be read
+}

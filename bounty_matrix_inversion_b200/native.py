@@ -157,7 +157,7 @@ class Engine:
         self.n_luts = luts.shape[0]
 
     def set_pbs_mode(self, mode: int):
-        """bootstrap kernel build: 0 automatic per launch size, 1 latency build, 2 throughput build"""
+        """bootstrap kernel build: 0 automatic per launch size, 1 latency build, 2 throughput build, 3 8-CTA split kernel"""
         _check(lib().bmi_ctx_set_pbs_mode(self._h, mode))
 
     def set_tma_stage(self, on: bool):

@@ -177,6 +177,10 @@ TOY_1024 = TfheParams("toy_n48_N1024", 48, 1, 1024, 8, 3, 4, 5, 2.0 ** 24, 2.0 *
 TOY_2048 = TfheParams("toy_n40_N2048", 40, 1, 2048, 12, 2, 4, 5, 2.0 ** 24, 2.0 ** 14)
 TOY_4096 = TfheParams("toy_n24_N4096", 24, 1, 4096, 23, 1, 6, 3, 2.0 ** 24, 2.0 ** 10)
 TOY_8192 = TfheParams("toy_n16_N8192", 16, 1, 8192, 15, 2, 4, 5, 2.0 ** 24, 2.0 ** 10)
+# one decomposition level (what every 128-bit set uses): exercises the l == 1 kernel paths at every polynomial size
+TOY_1024_L1 = TfheParams("toy_n40_N1024_l1", 40, 1, 1024, 22, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
+TOY_2048_L1 = TfheParams("toy_n32_N2048_l1", 32, 1, 2048, 22, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
+TOY_8192_L1 = TfheParams("toy_n16_N8192_l1", 16, 1, 8192, 24, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
 
 
 def _secure(name, n, N, bbl, bl, kbl, kl):
