@@ -56,34 +56,46 @@ size_t split_smem(const bmi_ctx* c) { return (size_t)5 * (c->p.N / 4) * 8 + (((s
 size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
 
 template <int L>
+constexpr int split_convert_e() { return L <= 12 ? 2 : L == 13 ? 3 : 4; }
+constexpr int kMaxClusterL = 13;   // largest polynomial the 2-CTA cluster kernels hold in shared memory; above: split kernel only
+
+template <int L>
 int setup_attrs(const bmi_ctx* c) {
-    constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
-    const int sm = (int)pbs_smem(c), sms = (int)pbs_smem_staged(c);
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-    if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
-    if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
     CK(cudaFuncSetAttribute(pbs_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
-    CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, (L <= 12 ? 2 : 3)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    CK(cudaFuncSetAttribute(polymul_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    CK(cudaFuncSetAttribute(polymul_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    CK(cudaFuncSetAttribute(polymul_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SplitCfg<L>::M * 8));
+    CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, split_convert_e<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    if constexpr (L <= kMaxClusterL) {
+        constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
+        const int sm = (int)pbs_smem(c), sms = (int)pbs_smem_staged(c);
+        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
+        if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
+        CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+        CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+        CK(cudaFuncSetAttribute(polymul_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+        CK(cudaFuncSetAttribute(polymul_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    }
     return BMI_OK;
 }
 
 // both layouts of the transform-domain key: [0] throughput build (E = 4), [1] latency build
 template <int L>
 int launch_convert(bmi_ctx* c, const u64* src, int64_t p0, int64_t polys, cudaStream_t st) {
-    constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
     const size_t off = (size_t)p0 * c->p.N;
-    bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, c->d_bsk[0] + off, c->d_tw, c->ninv);
-    bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, c->d_bsk[1] + off, c->d_tw, c->ninv);
-    constexpr int EC = L <= 12 ? 2 : 3;
-    bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, c->d_bsk[2] + off, c->d_tw, c->ninv);
-    c->launches += 3;
+    if constexpr (L <= kMaxClusterL) {
+        constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
+        bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, c->d_bsk[0] + off, c->d_tw, c->ninv);
+        bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, c->d_bsk[1] + off, c->d_tw, c->ninv);
+        c->launches += 2;
+    }
+    if (c->p.bsk_l == 1) {
+        constexpr int EC = split_convert_e<L>();
+        bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, c->d_bsk[2] + off, c->d_tw, c->ninv);
+        c->launches++;
+    }
     CK(cudaGetLastError());
     return BMI_OK;
 }
@@ -109,11 +121,23 @@ int64_t split_capacity(bmi_ctx* c) {
 }
 
 template <int L>
+int launch_split(bmi_ctx* c, PbsArgs a, int64_t total, cudaStream_t st) {
+    a.bsk_hat = c->d_bsk[2];
+    pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+template <int L>
 int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
-    constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
     const int64_t total = (int64_t)a.njobs * a.batch;
-    const unsigned grid = 2 * (unsigned)std::min<int64_t>(total, 1 << 20);      // one CTA pair per ciphertext
     const bool one = a.l == 1;
+    if constexpr (L > kMaxClusterL) {
+        return launch_split<L>(c, a, total, st);
+    } else {
+    constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
+    const unsigned grid = 2 * (unsigned)std::min<int64_t>(total, 1 << 20);      // one CTA pair per ciphertext
     // While the launch fits the CTA pairs the latency build keeps resident, latency wins; beyond one wave the
     // 16-coefficients-per-thread build (fewer shared-memory round trips, more ciphertexts per SM) does.
     int resident = 1;
@@ -121,13 +145,7 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
     const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
     // A handful of ciphertexts: spread each over an 8-CTA cluster (4 CTAs per polynomial), lowest latency.
-    if (one && (c->pbs_mode == 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) {
-        a.bsk_hat = c->d_bsk[2];
-        pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
-        c->launches++;
-        CK(cudaGetLastError());
-        return BMI_OK;
-    }
+    if (one && (c->pbs_mode == 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) return launch_split<L>(c, a, total, st);
     const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
     a.bsk_hat = c->d_bsk[latency ? 1 : 0];
     const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
@@ -142,21 +160,24 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
+    }
 }
 
 template <int L>
 int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, cudaStream_t st) {
-    constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
-    if (c->pbs_mode == 3) {
+    if (c->pbs_mode == 3 || L > kMaxClusterL) {
         polymul_split_kernel<L><<<4 * count, SplitCfg<L>::T, 3 * SplitCfg<L>::M * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
         c->launches++;
         CK(cudaGetLastError());
         return BMI_OK;
     }
-    if (c->pbs_mode == 1) polymul_kernel<L, EL><<<count, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
-    else polymul_kernel<L, ET><<<count, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
-    c->launches++;
-    CK(cudaGetLastError());
+    if constexpr (L <= kMaxClusterL) {
+        constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
+        if (c->pbs_mode == 1) polymul_kernel<L, EL><<<count, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
+        else polymul_kernel<L, ET><<<count, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     return BMI_OK;
 }
 
@@ -166,6 +187,7 @@ int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, 
         case 11: { constexpr int L = 11; return expr; }      \
         case 12: { constexpr int L = 12; return expr; }      \
         case 13: { constexpr int L = 13; return expr; }      \
+        case 14: { constexpr int L = 14; return expr; }      \
         default: set_error("unsupported polynomial size"); return BMI_EINVAL; \
     }
 
@@ -203,7 +225,8 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     if (p->k != 1) { set_error("kernels support GLWE dimension k == 1 only"); return BMI_EINVAL; }
     int logN = 0;
     while ((1 << logN) < p->N) logN++;
-    if ((1 << logN) != p->N || logN < 10 || logN > 13) { set_error("polynomial size must be 1024..8192"); return BMI_EINVAL; }
+    if ((1 << logN) != p->N || logN < 10 || logN > 14) { set_error("polynomial size must be 1024..16384"); return BMI_EINVAL; }
+    if (logN == 14 && p->bsk_l != 1) { set_error("N = 16384 runs on the 8-CTA split kernel, which needs one decomposition level"); return BMI_EINVAL; }
     if (p->bsk_bl * p->bsk_l > 63 || p->ksk_bl * p->ksk_l > 63 || p->ksk_bl > 30 || p->n < 1 || p->n > 4096) {
         set_error("unsupported decomposition / dimension");
         return BMI_EINVAL;
@@ -244,8 +267,10 @@ int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
     CK(cudaSetDevice(c->device));
     const int64_t polys = (int64_t)c->p.n * 2 * c->p.bsk_l * 2;
     const size_t bytes = (size_t)polys * c->p.N * 8;
-    for (int v = 0; v < 3; v++)
-        if (!c->d_bsk[v]) CK(cudaMalloc(&c->d_bsk[v], bytes));
+    for (int v = 0; v < 3; v++) {
+        const bool needed = v == 2 ? c->p.bsk_l == 1 : c->logN <= kMaxClusterL;
+        if (needed && !c->d_bsk[v]) CK(cudaMalloc(&c->d_bsk[v], bytes));
+    }
     // upload in slices through a bounded staging buffer, converting slice by slice
     const int64_t slice = std::min<int64_t>(polys, 4096);
     u64* stage = nullptr;
@@ -345,7 +370,7 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
 int bmi_pbs(bmi_ctx* c, const uint64_t* d_small, const int32_t* d_job_in, const int32_t* d_job_lut, const int32_t* d_job_out,
             uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
     if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
-    if (!c->d_bsk[0] || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
+    if (!(c->d_bsk[0] || c->d_bsk[2]) || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
     if (njobs == 0) return BMI_OK;
     PbsArgs a;
     a.bsk_hat = nullptr; a.tw = c->d_tw; a.twi = c->d_twi; a.luts = c->d_luts; a.small = d_small;

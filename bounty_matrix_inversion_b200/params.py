@@ -181,6 +181,7 @@ TOY_8192 = TfheParams("toy_n16_N8192", 16, 1, 8192, 15, 2, 4, 5, 2.0 ** 24, 2.0 
 TOY_1024_L1 = TfheParams("toy_n40_N1024_l1", 40, 1, 1024, 22, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
 TOY_2048_L1 = TfheParams("toy_n32_N2048_l1", 32, 1, 2048, 22, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
 TOY_8192_L1 = TfheParams("toy_n16_N8192_l1", 16, 1, 8192, 24, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
+TOY_16384_L1 = TfheParams("toy_n10_N16384_l1", 10, 1, 16384, 24, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
 
 
 def _secure(name, n, N, bbl, bl, kbl, kl):

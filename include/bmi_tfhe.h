@@ -32,7 +32,7 @@ extern "C" {
 typedef struct bmi_params {
     int32_t n;          /* small LWE dimension */
     int32_t k;          /* GLWE dimension (kernels support k == 1) */
-    int32_t N;          /* polynomial size, 1024 | 2048 | 4096 | 8192 */
+    int32_t N;          /* polynomial size, 1024 | 2048 | 4096 | 8192 | 16384 (16384: bsk_l == 1 only) */
     int32_t bsk_bl;     /* PBS decomposition base log */
     int32_t bsk_l;      /* PBS decomposition levels */
     int32_t ksk_bl;     /* keyswitch base log */
