@@ -10,7 +10,8 @@ batched lincomb -> keyswitch -> PBS launch group.  PBS/s = table lookups execute
   value : inputs (ciphertexts) already resident in HBM, CUDA-event timed
   e2e   : same step through Circuit.run(), i.e. HOST ciphertext buffers in, HOST ciphertext buffers out
   --impl reference : the CPU restatement (oracle/tfhe_oracle_fast.c, all host threads) on a bounded sample
-  --inversion n    : additionally time one encrypted n x n inversion (tests/golden/inv{n}_low.npz)
+  --inversion X    : additionally time one encrypted inversion (X = 2|3|4 -> tests/golden/inv{X}_low.npz, or a program
+                     name such as inv3_medium / inv4_high)
 
 Multi-GPU: launched by torchrun; the pairs are independent, so every rank takes its own `--pairs`
 lanes with replicated keys and no data-path collective ("weak" scaling).  The level-sharded
@@ -155,7 +156,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=24, help="QFloat pairs (batch lanes) per step and per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--inversion", type=int, default=0, help="also time one encrypted n x n inversion (2 or 3)")
+    ap.add_argument("--inversion", default="", help="also time one encrypted inversion: 2 | 3 | 4 (low precision) or a "
+                                                   "compiled program in tests/golden, e.g. inv3_medium, inv4_high")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -356,7 +358,8 @@ def time_inversion(n, fhe, PR, local, rank, world, dist):
     """one encrypted n x n QFloat inversion (low precision), levels sharded over the ranks when world > 1"""
     import torch
     from bounty_matrix_inversion_b200.fhe.program import Program
-    path = os.path.join(GOLDEN, f"inv{n}_low.npz")
+    name = f"inv{n}_low" if str(n).isdigit() else str(n)
+    path = os.path.join(GOLDEN, name + ".npz")
     z, prog = np.load(path), Program.load(path)
     c = fhe.Circuit.from_program(prog, configuration=fhe.Configuration(device=local, seed=77))
     c.keygen()
@@ -375,7 +378,7 @@ def time_inversion(n, fhe, PR, local, rank, world, dist):
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = bool(np.array_equal(c.decrypt(out), want))
-    return {"n": n, "precision": "low", "wall_s": float(t.item()), "pbs": prog.n_pbs, "levels": len(prog.levels),
+    return {"program": name, "n": int(z["meta_n"]), "qfloat_len": int(z["meta_qfloat_len"]), "wall_s": float(t.item()), "pbs": prog.n_pbs, "levels": len(prog.levels),
             "params": c.params.name, "digits_match_reference_clear_path": ok, "world": world}
 
 

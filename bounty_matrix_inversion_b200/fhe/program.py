@@ -79,16 +79,18 @@ class Program:
 
     @classmethod
     def load(cls, path):
-        z = np.load(path, allow_pickle=False)
+        with np.load(path, allow_pickle=False) as npz:
+            z = {k: npz[k] for k in npz.files}            # NpzFile decompresses on every access: read each array once
         ks, nz, pb = z["ks_counts"], z["nz_counts"], z["pbs_counts"]
         ko, no, po = np.cumsum(np.r_[0, ks]), np.cumsum(np.r_[0, nz]), np.cumsum(np.r_[0, pb])
         ro = np.cumsum(np.r_[0, ks + 1])
+        row_ptr, idx, coef, konst = (z["row_ptr"].astype(np.int32), z["idx"].astype(np.int32), z["coef"].astype(np.int64),
+                                     z["konst"].astype(np.int64))
+        job_ks, job_lut, job_out = z["job_ks"].astype(np.int32), z["job_lut"].astype(np.int32), z["job_out"].astype(np.int32)
         levels = []
         for i in range(len(ks)):
-            levels.append(Level(z["row_ptr"][ro[i]:ro[i + 1]].astype(np.int32), z["idx"][no[i]:no[i + 1]].astype(np.int32),
-                                z["coef"][no[i]:no[i + 1]].astype(np.int64), z["konst"][ko[i]:ko[i + 1]].astype(np.int64),
-                                z["job_ks"][po[i]:po[i + 1]].astype(np.int32), z["job_lut"][po[i]:po[i + 1]].astype(np.int32),
-                                z["job_out"][po[i]:po[i + 1]].astype(np.int32)))
+            levels.append(Level(row_ptr[ro[i]:ro[i + 1]], idx[no[i]:no[i + 1]], coef[no[i]:no[i + 1]], konst[ko[i]:ko[i + 1]],
+                                job_ks[po[i]:po[i + 1]], job_lut[po[i]:po[i + 1]], job_out[po[i]:po[i + 1]]))
         import ast
         prog = cls(int(z["width"]), int(z["n_inputs"]), int(z["n_slots"]), z["input_slots"].astype(np.int32), levels,
                    z["out_row_ptr"].astype(np.int32), z["out_idx"].astype(np.int32), z["out_coef"].astype(np.int64),
