@@ -36,6 +36,7 @@ struct bmi_ctx {
     int num_sms = 148;
     int64_t launches = 0;
     int split_clusters = -1;   // resident 8-CTA clusters of the split kernel (queried once)
+    bool split_async = true;  // split kernel synchronised by mbarriers + st.async (BMI_SPLIT_ASYNC=0: cluster barriers)
     bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
     int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel
     // scratch for the host-buffer convenience path
@@ -52,7 +53,7 @@ constexpr int kMaxSmem = 227 * 1024;   // dynamic shared memory a CTA can opt in
 
 size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
 
-size_t split_smem(const bmi_ctx* c) { return (size_t)5 * (c->p.N / 4) * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
+size_t split_smem(const bmi_ctx* c) { return (size_t)6 * (c->p.N / 4) * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
 size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
 
 template <int L>
@@ -62,6 +63,7 @@ constexpr int kMaxClusterL = 13;   // largest polynomial the 2-CTA cluster kerne
 template <int L>
 int setup_attrs(const bmi_ctx* c) {
     CK(cudaFuncSetAttribute(pbs_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_split_async_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
     CK(cudaFuncSetAttribute(polymul_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SplitCfg<L>::M * 8));
     CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, split_convert_e<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     if constexpr (L <= kMaxClusterL) {
@@ -123,7 +125,8 @@ int64_t split_capacity(bmi_ctx* c) {
 template <int L>
 int launch_split(bmi_ctx* c, PbsArgs a, int64_t total, cudaStream_t st) {
     a.bsk_hat = c->d_bsk[2];
-    pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
+    if (c->split_async) pbs_split_async_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
+    else pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
@@ -246,6 +249,7 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     CK(cudaMemcpy(c->d_tw, tw.data(), p->N * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_twi, twi.data(), p->N * 8, cudaMemcpyHostToDevice));
     if (const char* v = getenv("BMI_TMA_STAGE")) c->tma_stage = v[0] == '1';
+    if (const char* v = getenv("BMI_SPLIT_ASYNC")) c->split_async = v[0] != '0';
     int rc = do_setup(c);
     if (rc) { delete c; return rc; }
     *out = c;

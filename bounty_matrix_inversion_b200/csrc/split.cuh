@@ -101,6 +101,31 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SplitCfg<L>::T) poly
 }
 
 // ----------------------------------------------------------------------------
+// DSMEM signalling without cluster-wide barriers: data is pushed with st.async, which counts its bytes on an
+// mbarrier in the DESTINATION CTA; the consumer waits on its own mbarrier for the bytes it expects.  No release
+// fence on the producer side (the cluster-barrier version spent 29 % of its issue slots in `membar`, see profiles/).
+__device__ __forceinline__ u32 map_shared_u32(const void* p, u32 rank) {
+    u32 out;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_addr(p)), "r"(rank));
+    return out;
+}
+__device__ __forceinline__ void st_async_u64(u32 remote_addr, u64 v, u32 remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u64 [%0], %1, [%2];"
+                 ::"r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(u32 remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(u64* bar, u32 parity) {
+    asm volatile("{ .reg .pred p;\n"
+                 "WC: mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DC;\n bra WC;\n DC: }" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// ----------------------------------------------------------------------------
 // key conversion for the split layout: [poly][r][e][t] <- transform value at position (r*T + t)*4 + e
 template <int L, int E>
 __global__ void __launch_bounds__(NttCfg<L, E>::T) bsk_convert_split_kernel(const u64* __restrict__ src, u64* __restrict__ dst,
@@ -211,4 +236,172 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
         }
     }
     cluster_sync_all();               // nobody exits while its shared memory may still be read
+}
+
+
+// ----------------------------------------------------------------------------
+// same bootstrap, synchronised by mbarriers instead of cluster barriers.  Per CMUX and CTA:
+//   acc_bar  (4 arrivals)  every CTA of the group has finished updating its accumulator  -> rotated reads may start
+//   fwd_bar  (M*8 bytes)   the forward all-to-all has landed in gbuf
+//   rcv_bar  (M*8 bytes)   the partner polynomial's partial sums have landed in recv[parity]
+//   inv_bar  (M*8 bytes)   the inverse all-to-all has landed in lbuf
+// Buffer reuse is safe without back-pressure: a CTA can only reach the next write of a buffer after waiting for data
+// that its reader sends AFTER the read (gbuf, lbuf, acc), or the buffer is double-buffered (recv).
+// (Folding the partial-sum exchange into the inverse all-to-all via linearity of the inverse transform was tried:
+//  same time, more DSMEM traffic -- not kept.)
+template <int L>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) pbs_split_async_kernel(const PbsArgs a) {
+    using C = SplitCfg<L>;
+    using LC = typename C::Local;
+    constexpr int N = C::N, M = C::M, T = C::T;
+    extern __shared__ u64 smem[];
+    u64* acc = smem;
+    u64* buf = smem + M;
+    u64* gbuf = smem + 2 * M;
+    u64* lbuf = smem + 3 * M;
+    u64* recv = smem + 4 * M;         // [2][M]
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 6 * M);
+    __shared__ __align__(8) u64 bars[4];      // acc, fwd, rcv, inv
+    const int tid = threadIdx.x;
+    const u32 rank = cluster_rank(), c = rank >> 2, r = rank & 3, group0 = c << 2, partner = ((c ^ 1) << 2) + r;
+    const int n = a.n, bl = a.bl;
+    const int total = a.njobs * a.batch;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 4);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        mbar_init(&bars[3], 1);
+    }
+    __syncthreads();
+    cluster_sync_all();               // every CTA's barriers exist before anyone signals them
+    u32 gbuf_r[4], lbuf_r[4], fwd_bar_r[4], inv_bar_r[4], acc_bar_r[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        gbuf_r[g] = map_shared_u32(gbuf, group0 + g);
+        lbuf_r[g] = map_shared_u32(lbuf, group0 + g);
+        acc_bar_r[g] = map_shared_u32(&bars[0], group0 + g);
+        fwd_bar_r[g] = map_shared_u32(&bars[1], group0 + g);
+        inv_bar_r[g] = map_shared_u32(&bars[3], group0 + g);
+    }
+    const u32 recv_r = map_shared_u32(recv, partner), rcv_bar_r = map_shared_u32(&bars[2], partner);
+    u32 ph_acc = 0, ph = 0;           // ph: common parity of fwd/rcv/inv (each used exactly once per CMUX)
+
+    for (int f = blockIdx.x >> 3; f < total; f += gridDim.x >> 3) {
+        const int q0 = f / a.batch, b0 = f - q0 * a.batch;
+        const u64* in = a.small + ((size_t)a.job_in[q0] * a.batch + b0) * (n + 1);
+        const u64* lut = a.luts + (size_t)a.job_lut[q0] * N;
+        u64* out = a.out + ((size_t)a.job_out[q0] * a.batch + b0) * (N + 1);
+
+        for (int i = tid; i < n; i += T) rot[i] = (unsigned short)modswitch(in[i], L);
+        {
+            const u32 r0 = (2 * N - modswitch(in[n], L)) & (2 * N - 1);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lc = q * T + tid, gi = lc * 4 + (int)r;
+                const u32 u = (gi + 2 * N - r0) & (2 * N - 1);
+                acc[lc] = c == 0 ? 0 : (u < N ? lut[u] : fneg(lut[u - N]));
+            }
+        }
+        __syncthreads();
+        if (tid < 4) mbar_arrive_remote(acc_bar_r[tid]);      // my accumulator is ready
+
+        for (int i = 0; i < n; i++) {
+            const u32 at = rot[i];
+            if (at == 0) continue;
+            if (tid == 0) {           // post what this CMUX will receive
+                mbar_expect(&bars[1], M * 8);
+                mbar_expect(&bars[2], M * 8);
+                mbar_expect(&bars[3], M * 8);
+            }
+            mbar_wait_cluster(&bars[0], ph_acc);
+            ph_acc ^= 1;
+            u64 x[4];
+            {
+                const u64* src = cluster_map(acc, group0 + ((r - at) & 3));
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int lc = q * T + tid, gi = lc * 4 + (int)r;
+                    const u32 u = (gi + 2 * N - at) & (2 * N - 1);
+                    const u64 v = src[(u & (N - 1)) >> 2];
+                    const u64 rv = u < N ? v : fneg(v);
+                    x[q] = digit_of(round_top(fsub(rv, acc[lc]), bl), bl, 1, 1);
+                }
+            }
+            // ---- forward: local stages, all-to-all, two block stages
+            ntt_forward<C::LL, kSplitE>(x, buf, a.tw, tid);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int jl = slot_index<C::LL, kSplitE>(LC::NPASS - 1, q, tid);
+                const int dst = jl >> (C::LL - 2), b = jl & (T - 1);
+                st_async_u64(gbuf_r[dst] + (u32)(b * 4 + (int)r) * 8, x[q], fwd_bar_r[dst]);
+            }
+            mbar_wait(&bars[1], ph);
+            {
+                const ulonglong2 v01 = *reinterpret_cast<const ulonglong2*>(gbuf + tid * 4);
+                const ulonglong2 v23 = *reinterpret_cast<const ulonglong2*>(gbuf + tid * 4 + 2);
+                x[0] = v01.x; x[1] = v01.y; x[2] = v23.x; x[3] = v23.y;
+            }
+            const int blk = (int)r * T + tid;
+            {
+                const u64 wa = __ldg(a.tw + (1 << (L - 2)) + blk);
+                butterfly<false>(x[0], x[2], wa);
+                butterfly<false>(x[1], x[3], wa);
+                butterfly<false>(x[0], x[1], __ldg(a.tw + (1 << (L - 1)) + 2 * blk));
+                butterfly<false>(x[2], x[3], __ldg(a.tw + (1 << (L - 1)) + 2 * blk + 1));
+            }
+            // ---- pointwise products; the partner polynomial's share goes to the partner CTA
+            const u64* g = a.bsk_hat + ((size_t)i * 2 + c) * 2 * N + (size_t)r * M;
+            u64 own[4];
+            const u32 rbase = recv_r + (ph ? (u32)M * 8 : 0);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                st_async_u64(rbase + (u32)(e * T + tid) * 8, fmul_c(x[e], __ldg(g + (size_t)(c ^ 1) * N + e * T + tid)), rcv_bar_r);
+                own[e] = fmul_l(x[e], __ldg(g + (size_t)c * N + e * T + tid));
+            }
+            mbar_wait(&bars[2], ph);
+            {
+                const u64* rb = recv + (ph ? M : 0);
+#pragma unroll
+                for (int e = 0; e < 4; e++) own[e] = fadd_l(own[e], rb[e * T + tid]);
+            }
+            // ---- inverse: two block stages, all-to-all, local stages
+            butterfly<true>(own[0], own[1], __ldg(a.twi + (1 << (L - 1)) + 2 * blk));
+            butterfly<true>(own[2], own[3], __ldg(a.twi + (1 << (L - 1)) + 2 * blk + 1));
+            {
+                const u64 wa = __ldg(a.twi + (1 << (L - 2)) + blk);
+                butterfly<true>(own[0], own[2], wa);
+                butterfly<true>(own[1], own[3], wa);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) st_async_u64(lbuf_r[e] + (u32)blk * 8, own[e], inv_bar_r[e]);
+            mbar_wait(&bars[3], ph);
+            ph ^= 1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) own[q] = lbuf[slot_index<C::LL, kSplitE>(LC::NPASS - 1, q, tid)];
+            ntt_inverse<C::LL, kSplitE>(own, buf, a.twi, tid);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lc = q * T + tid;
+                acc[lc] = fcanon(fadd_l(own[q], acc[lc]));
+            }
+            __syncthreads();
+            if (tid < 4) mbar_arrive_remote(acc_bar_r[tid]);
+        }
+
+        mbar_wait_cluster(&bars[0], ph_acc);      // consume the last "accumulator ready" round
+        ph_acc ^= 1;
+        if (c == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int lc = q * T + tid, gi = lc * 4 + (int)r;
+                const u64 v = acc[lc];
+                if (gi == 0) out[0] = v; else out[N - gi] = fneg(v);
+            }
+        } else if (r == 0 && tid == 0) {
+            out[N] = acc[0];
+        }
+        __syncthreads();              // extraction done before the next ciphertext overwrites acc / rot
+    }
+    cluster_sync_all();
 }

@@ -30,7 +30,7 @@ def main():
         w = 3
         luts = np.stack([PR.lut_polynomial([PR.encode(t, w) for t in range(8)], w, prm.N)])
         eng.load_luts(luts)
-        for mode, count in [(m, c) for m in (0,) for c in (1, 8, 16, 18, 24, 32, 74)]:
+        for mode, count in [(m, c) for m in (0, 1, 2, 3) for c in (1, 8, 74, 148, 296, 592, 1184)]:
             eng.set_pbs_mode(mode)
             cts = keys.encrypt([PR.encode(i % 8, w) for i in range(min(count, 16))])
             cts = np.tile(cts, (count // len(cts) + 1, 1))[:count]
