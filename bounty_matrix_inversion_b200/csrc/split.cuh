@@ -21,7 +21,6 @@ struct SplitCfg {
     using Local = NttCfg<L - 2, kSplitE>;
 };
 
-__device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
 
 // x: 4 registers in pass-0 layout of the local transform (slot q <-> local coefficient q*T + tid <-> global
 // coefficient (q*T + tid)*4 + r).  Out: y[e] = transform value at position (r*T + tid)*4 + e.
@@ -98,31 +97,6 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(SplitCfg<L>::T) poly
     split_inverse<L>(x, buf, lbuf, twi, tid, 0, r);
 #pragma unroll
     for (int q = 0; q < 4; q++) c[off + (q * C::T + tid) * 4 + (int)r] = fcanon(x[q]);
-}
-
-// ----------------------------------------------------------------------------
-// DSMEM signalling without cluster-wide barriers: data is pushed with st.async, which counts its bytes on an
-// mbarrier in the DESTINATION CTA; the consumer waits on its own mbarrier for the bytes it expects.  No release
-// fence on the producer side (the cluster-barrier version spent 29 % of its issue slots in `membar`, see profiles/).
-__device__ __forceinline__ u32 map_shared_u32(const void* p, u32 rank) {
-    u32 out;
-    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_addr(p)), "r"(rank));
-    return out;
-}
-__device__ __forceinline__ void st_async_u64(u32 remote_addr, u64 v, u32 remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u64 [%0], %1, [%2];"
-                 ::"r"(remote_addr), "l"(v), "r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect(u64* bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(u32 remote_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(u64* bar, u32 parity) {
-    asm volatile("{ .reg .pred p;\n"
-                 "WC: mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-                 "@p bra DC;\n bra WC;\n DC: }" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
 // ----------------------------------------------------------------------------
