@@ -44,6 +44,7 @@ struct bmi_ctx {
     int *w_idx = nullptr, *w_lut = nullptr;
     int64_t w_cap = 0;
     u64* ks_partial = nullptr;   // per-slice keyswitch sums (small batches)
+    u64* d_ks_corr = nullptr;    // [n+1] B/2 * column sums of the keyswitch key (digits are used shifted by B/2)
     size_t ks_partial_cap = 0;
 };
 
@@ -230,7 +231,9 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     while ((1 << logN) < p->N) logN++;
     if ((1 << logN) != p->N || logN < 10 || logN > 14) { set_error("polynomial size must be 1024..16384"); return BMI_EINVAL; }
     if (logN == 14 && p->bsk_l != 1) { set_error("N = 16384 runs on the 8-CTA split kernel, which needs one decomposition level"); return BMI_EINVAL; }
-    if (p->bsk_bl * p->bsk_l > 63 || p->ksk_bl * p->ksk_l > 63 || p->ksk_bl > 30 || p->n < 1 || p->n > 4096) {
+    int ks_rows_log = 0;
+    while ((1LL << ks_rows_log) < (long long)p->k * p->N * p->ksk_l) ks_rows_log++;
+    if (p->bsk_bl * p->bsk_l > 63 || p->ksk_bl * p->ksk_l > 63 || ks_rows_log + p->ksk_bl > 32 || p->n < 1 || p->n > 4096) {
         set_error("unsupported decomposition / dimension");
         return BMI_EINVAL;
     }
@@ -261,7 +264,7 @@ int bmi_ctx_destroy(bmi_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk[0]); cudaFree(c->d_bsk[1]); cudaFree(c->d_bsk[2]); cudaFree(c->d_ksk); cudaFree(c->d_luts);
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
-    cudaFree(c->ks_partial);
+    cudaFree(c->ks_partial); cudaFree(c->d_ks_corr);
     delete c;
     return BMI_OK;
 }
@@ -296,6 +299,11 @@ int bmi_ctx_load_ksk(bmi_ctx* c, const uint64_t* h_ksk) {
     const size_t bytes = (size_t)c->p.k * c->p.N * c->p.ksk_l * (c->p.n + 1) * 8;
     if (!c->d_ksk) CK(cudaMalloc(&c->d_ksk, bytes));
     CK(cudaMemcpy(c->d_ksk, h_ksk, bytes, cudaMemcpyHostToDevice));
+    if (!c->d_ks_corr) CK(cudaMalloc(&c->d_ks_corr, (size_t)(c->p.n + 1) * 8));
+    keyswitch_corr_kernel<<<(c->p.n + 1 + 255) / 256, 256>>>(c->d_ksk, c->d_ks_corr, c->p.k * c->p.N * c->p.ksk_l, c->p.n, c->p.ksk_bl);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     return BMI_OK;
 }
 
@@ -357,13 +365,13 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
     }
     dim3 grid(cols, tiles, slices);
     const size_t smem = (size_t)KS_CHUNK * c->p.ksk_l * KS_JT * sizeof(int);
-    keyswitch_kernel<<<grid, KS_COLS, smem, (cudaStream_t)stream>>>(d_in, c->d_ksk, d_out, c->ks_partial, (int)count, kN, c->p.n,
+    keyswitch_kernel<<<grid, KS_COLS, smem, (cudaStream_t)stream>>>(d_in, c->d_ksk, c->d_ks_corr, d_out, c->ks_partial, (int)count, kN, c->p.n,
                                                                    c->p.ksk_bl, c->p.ksk_l, slice);
     c->launches++;
     CK(cudaGetLastError());
     if (slices > 1) {
         const size_t elems = (size_t)count * (c->p.n + 1);
-        keyswitch_finish_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, c->ks_partial, d_out, (int)count,
+        keyswitch_finish_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, c->ks_partial, c->d_ks_corr, d_out, (int)count,
                                                                                                   kN, c->p.n, slices);
         c->launches++;
         CK(cudaGetLastError());
