@@ -139,6 +139,9 @@ def run_reference(args, rank, world):
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1)", "data": "synthetic",
             "config": {"workload": "qfloat_microbench_4096pairs_base2_medium", "ops": "add,mul,div",
+                       "pbs_per_pair": sum(p.n_pbs for p, _, _ in progs.values()),
+                       "params": {op: __import__("bounty_matrix_inversion_b200.params", fromlist=["x"]).for_width(
+                           progs[op][0].width, progs[op][0].nu2).name for op in OPS},
                        "note": "concrete-python (the reference's FHE runtime) is not installable here; this arm times the "
                                "CPU restatement of the same keyswitch+PBS path on the workload's parameter sets"},
             "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": threads, "kind": "port",

@@ -100,23 +100,38 @@ class Program:
         return prog
 
     # ------------------------------------------------------------ clear evaluation
-    def evaluate_clear(self, inputs: np.ndarray) -> np.ndarray:
+    def evaluate_clear(self, inputs: np.ndarray, strict: bool = True):
         """run the levelled program on clear integers (what the ciphertexts hold); inputs [n_inputs] or
-        [batch][n_inputs] -> outputs shaped out_shape (with a leading batch axis if given)"""
+        [batch][n_inputs] -> outputs shaped out_shape (with a leading batch axis if given).
+        A lookup input outside the W-bit message space means the encrypted run would read a wrong table entry
+        (the value left the ranges seen on the compile-time inputset): strict raises OverflowError, otherwise the
+        result is (outputs, per-lane bool mask of such lanes) with the offending inputs wrapped like the ciphertext would."""
         x = np.asarray(inputs, dtype=np.int64)
         single = x.ndim == 1
         x = np.atleast_2d(x)
         B, W = x.shape[0], self.width
         vals = np.zeros((self.n_slots, B), np.int64)
         vals[self.input_slots] = x.T
+        bad = np.zeros(B, bool)
         for lv in self.levels:
             ks = _csr_apply(lv.row_ptr, lv.idx, lv.coef, lv.konst, vals)
             if ks.size and (ks.min() < 0 or ks.max() >= (1 << W)):
-                raise OverflowError(f"lookup input outside the {W}-bit message space: [{ks.min()}, {ks.max()}]")
+                if strict:
+                    raise OverflowError(f"lookup input outside the {W}-bit message space: [{ks.min()}, {ks.max()}]")
+                oob = (ks < 0) | (ks >= (1 << W))
+                bad |= oob.any(axis=0)
+                # what the bootstrap does: message mod 2^(W+1); upper half reads the negated table (negacyclic)
+                m = np.mod(ks, 1 << (W + 1))
+                neg = m >= (1 << W)
+                t = self.tables[lv.job_lut[:, None], np.where(neg, m - (1 << W), m)[lv.job_ks]]
+                vals[lv.job_out] = np.where(neg[lv.job_ks], -t, t)
+                continue
             vals[lv.job_out] = self.tables[lv.job_lut[:, None], ks[lv.job_ks]]
         out = _csr_apply(self.out_row_ptr, self.out_idx, self.out_coef, self.out_konst, vals)
         out = out.T.reshape((B,) + tuple(self.out_shape))
-        return out[0] if single else out
+        if strict:
+            return out[0] if single else out
+        return (out[0], bad[0]) if single else (out, bad)
 
 
 def _csr_apply(row_ptr, idx, coef, konst, vals):

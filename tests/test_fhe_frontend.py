@@ -144,3 +144,22 @@ def test_program_roundtrip(tmp_path):
     x = rng.integers(0, 4, (5, 6))
     assert np.array_equal(q.evaluate_clear(x), c.program.evaluate_clear(x))
     assert q.stats == c.program.stats
+
+
+def test_slack_bits_widen_the_message_space():
+    fn = lambda x, y: (x + y) // 2
+    base = compile_(fn, pairs(0, 4, (2,)))
+    wide = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(
+        pairs(0, 4, (2,)), fhe.Configuration(tfhe_params=PR.TOY_1024, slack_bits=1))
+    assert wide.program.width == base.program.width + 1
+    x, y = np.array([3, 1]), np.array([3, 2])
+    assert np.array_equal(wide.simulate(x, y), fn(x, y))
+
+
+def test_non_strict_evaluation_flags_out_of_range_lanes():
+    c = compile_(lambda x, y: (x + y) // 2, pairs(0, 4, (2,)))        # sums 0..6 seen -> 3-bit window
+    inside, outside = np.array([[3, 3, 3, 3]]), np.array([[3, 3, 40, 40]])
+    out, bad = c.program.evaluate_clear(np.concatenate([inside, outside]), strict=False)
+    assert list(bad) == [False, True] and np.array_equal(out[0], [3, 3])
+    with pytest.raises(OverflowError):
+        c.program.evaluate_clear(outside[0])
