@@ -86,19 +86,32 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+_CPU_CTX = {}
+
+
+def cpu_context(progs):
+    """keys and transform-domain key of the CPU restatement, built once per process"""
+    if not _CPU_CTX:
+        from bounty_matrix_inversion_b200 import native, params as PR
+        from oracle import oracle as orc
+        orc.build()
+        for op in OPS:
+            prog = progs[op][0]
+            prm = PR.for_width(prog.width, prog.nu2)
+            keys = native.ClientKeys(prm, seed=11)
+            _CPU_CTX[op] = (prm, keys, orc.Fast(prm, keys.bsk, keys.ksk), prog.lut_polynomials(prm.N)[:1])
+    return _CPU_CTX
+
+
 def cpu_sample(progs, threads, seconds_hint=15.0):
     """time the CPU restatement (keyswitch + PBS, all host threads) on a bounded sample of the workload's lookups"""
-    from bounty_matrix_inversion_b200 import native, params as PR
-    from oracle import oracle as orc
-    orc.build()
+    from bounty_matrix_inversion_b200 import params as PR
+    ctx = cpu_context(progs)
     total_pbs = sum(p.n_pbs for p, _, _ in progs.values())
     done, spent, parts = 0, 0.0, []
     for op in OPS:
         prog = progs[op][0]
-        prm = PR.for_width(prog.width, prog.nu2)
-        keys = native.ClientKeys(prm, seed=11)
-        fast = orc.Fast(prm, keys.bsk, keys.ksk)
-        luts = prog.lut_polynomials(prm.N)[:1]
+        prm, keys, fast, luts = ctx[op]
         share = prog.n_pbs / total_pbs
         count = threads
         cts = keys.encrypt([PR.encode(i % 2, prog.width) for i in range(count)])
