@@ -3,14 +3,16 @@ import os
 import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB = os.path.join(CSRC, "libbmi_tfhe.so")
+LIB = os.environ.get("BMI_TFHE_LIB") or os.path.join(CSRC, "libbmi_tfhe.so")   # override: kernel-variant experiments
 SOURCES = ["engine.cu", "client.cpp"]
-HEADERS = ["field.cuh", "ntt.cuh", "kernels.cuh", "host_common.h", "../../include/bmi_tfhe.h"]
+HEADERS = ["field.cuh", "ntt.cuh", "kernels.cuh", "split.cuh", "host_common.h", "../../include/bmi_tfhe.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
 def stale():
+    if os.environ.get("BMI_TFHE_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

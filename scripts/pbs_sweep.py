@@ -1,5 +1,6 @@
 """Raw keyswitch / PBS batch-size sweep on one GPU (CUDA-event timing).  usage: pbs_sweep.py [w ...]"""
 import json
+import os
 import sys
 import time
 
@@ -30,7 +31,9 @@ def main():
         w = 3
         luts = np.stack([PR.lut_polynomial([PR.encode(t, w) for t in range(8)], w, prm.N)])
         eng.load_luts(luts)
-        for mode, count in [(m, c) for m in (0, 1, 2, 3) for c in (1, 8, 74, 148, 296, 592, 1184)]:
+        modes = [int(v) for v in os.environ.get("SWEEP_MODES", "0,1,2,3").split(",")]
+        counts = [int(v) for v in os.environ.get("SWEEP_COUNTS", "1,8,74,148,296,592,1184").split(",")]
+        for mode, count in [(m, c) for m in modes for c in counts]:
             eng.set_pbs_mode(mode)
             cts = keys.encrypt([PR.encode(i % 8, w) for i in range(min(count, 16))])
             cts = np.tile(cts, (count // len(cts) + 1, 1))[:count]
