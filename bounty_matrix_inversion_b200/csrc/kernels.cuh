@@ -27,8 +27,8 @@ struct PbsArgs {
 template <int L>
 constexpr int latency_e() { return L <= 11 ? BMI_LAT_E11 : L == 12 ? BMI_LAT_E12 : 3; }
 #ifndef BMI_TP_E11
-#define BMI_TP_E11 2
-#define BMI_TP_B11 2
+#define BMI_TP_E11 3
+#define BMI_TP_B11 4
 #define BMI_TP_E12 3
 #define BMI_TP_B12 2
 #define BMI_TP_E13 3

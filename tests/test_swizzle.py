@@ -27,7 +27,7 @@ def cols_from_source(L, E):
 
 def test_every_instantiated_transform_is_conflict_free():
     configs = [(L, 4) for L in (10, 11, 12, 13)]                 # first-generation 16-per-thread transforms
-    configs += [(10, 2), (11, 2), (12, 2), (12, 3), (13, 3)]     # latency / throughput builds
+    configs += [(10, 2), (11, 2), (12, 2), (10, 3), (11, 3), (12, 3), (13, 3)]     # latency / throughput builds
     configs += [(8, 2), (9, 2), (10, 2), (11, 2)]                # local transforms of the 8-CTA split kernel
     for L, E in configs:
         assert conflict_free(L, E, cols_from_source(L, E)), (L, E)
