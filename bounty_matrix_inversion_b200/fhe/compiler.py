@@ -15,7 +15,8 @@ from .program import Program, lower
 
 class Configuration:
     """accepts Concrete's keyword options; the ones this engine understands:
-    tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, seed, device"""
+    tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, seed, device,
+    multiplication ("auto" | "quarter_square", see tracing.Trace)"""
 
     def __init__(self, **options):
         self.options = dict(options)
@@ -24,6 +25,7 @@ class Configuration:
         self.slack_bits = options.get("slack_bits", 0)
         self.seed = options.get("seed", 0x5EED)
         self.device = options.get("device", 0)
+        self.multiplication = options.get("multiplication", "auto")
 
     def fork(self, **options):
         merged = dict(self.options)
@@ -53,7 +55,7 @@ class Compiler:
                 raise NotImplementedError(f"parameter '{n}': only 'encrypted' inputs are supported")
         self.names = names
 
-    def trace(self, inputset):
+    def trace(self, inputset, multiplication="auto"):
         samples = [s if isinstance(s, (tuple, list)) else (s,) for s in inputset]
         if not samples:
             raise ValueError("inputset is empty")
@@ -61,7 +63,7 @@ class Compiler:
             if len(s) != len(self.names):
                 raise ValueError("inputset sample arity does not match the function")
         cols = [np.stack([np.asarray(s[i], dtype=np.int64) for s in samples]) for i in range(len(self.names))]
-        trace = tracing.Trace(len(samples))
+        trace = tracing.Trace(len(samples), multiplication)
         with trace:
             args = []
             for col in cols:
@@ -87,7 +89,7 @@ class Compiler:
         if options:
             cfg = cfg.fork(**options)
         t0 = time.time()
-        trace, flat_out, out_shapes, in_shapes = self.trace(inputset)
+        trace, flat_out, out_shapes, in_shapes = self.trace(inputset, cfg.multiplication)
         t1 = time.time()
         n_out = len(flat_out)
         prog = lower(trace, flat_out, (n_out,), slack_bits=cfg.slack_bits)

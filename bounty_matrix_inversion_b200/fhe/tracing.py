@@ -33,7 +33,14 @@ def current():
 class Trace:
     """collects the table lookups emitted while the circuit function runs"""
 
-    def __init__(self, n_samples: int):
+    def __init__(self, n_samples: int, multiplication: str = "auto"):
+        """multiplication: how ciphertext * ciphertext is lowered.  "quarter_square" = two lookups
+        ((a+b)^2/4 - (a-b)^2/4, Concrete's lowering); "auto" = ONE lookup on the packed value when one factor is a
+        bit and the other spans at most four values on the inputset (three quarters of the reference's lookups are
+        such products), quarter squares otherwise.  Same results either way."""
+        if multiplication not in ("auto", "quarter_square"):
+            raise ValueError("multiplication must be 'auto' or 'quarter_square'")
+        self.multiplication = multiplication
         self.n_samples = n_samples
         self.n_inputs = 0
         self.jobs = []          # Job objects, index = base_id - n_inputs once inputs are frozen
@@ -214,12 +221,42 @@ def s_mul(a, b, group=None):
         if isinstance(b, Lazy):
             return b.then(lambda x, c=a: x * c, group or Group())
         return _scale(b, a)
-    # ciphertext * ciphertext = ((a+b)^2 - (a-b)^2) / 4: two table lookups, as Concrete lowers it
     a, b = _aff(a), _aff(b)
     g = group or Group()
+    packed = _packed_product(a, b, g)
+    if packed is not None:
+        return packed
+    # ciphertext * ciphertext = ((a+b)^2 - (a-b)^2) / 4: two table lookups, as Concrete lowers it
     plus = Lazy(_lin(a, b, 1), _sq4, g.child("sum")).aff()
     minus = Lazy(_lin(a, b, -1), _sq4, g.child("difference")).aff()
     return _lin(plus, minus, -1)
+
+
+_PACK_SPAN = 8      # packed products stay within 3 message bits, below every circuit's width
+
+
+def _packed_product(a: Aff, b: Aff, g: Group):
+    """bit * small value as ONE lookup on x = (v - lo) + bit * R, R = span of v: f(x) = x >= R ? x - R + lo : 0"""
+    tr = current()
+    if tr is None or tr.multiplication != "auto":
+        return None
+    is_bit = lambda t: t.vals.min() >= 0 and t.vals.max() <= 1
+    if is_bit(b):
+        v, bit = a, b
+    elif is_bit(a):
+        v, bit = b, a
+    else:
+        return None
+    lo, hi = int(v.vals.min()), int(v.vals.max())
+    if 2 * (hi - lo + 1) > _PACK_SPAN:
+        return None
+    if 2 * (hi - lo + 3) <= _PACK_SPAN:        # room for a guard value on each side of the observed range
+        lo, hi = lo - 1, hi + 1
+    R = hi - lo + 1
+    x = _lin(Aff(v.terms, v.const - lo, v.vals - lo), _scale(bit, R), 1)
+    grp = g.child("packed")
+    grp.see(np.array([0, 2 * R - 1]))           # the declared domain, not only what the inputset happened to hit
+    return Lazy(x, lambda t, R=R, lo=lo: np.where(t >= R, t - R + lo, 0), grp).aff()
 
 
 def s_univariate(a, fn, group=None):

@@ -100,6 +100,7 @@ def qfloat_op_case(op, precision, n_golden=16, seed=1):
 CASES = {
     "inv2_low": lambda: inversion_case(2, "low"),
     "inv2_low_tensorized": lambda: inversion_case(2, "low", tensorize=True),
+    "inv2_low_quarter_square": lambda: inversion_case(2, "low"),       # compiled with Concrete's two-lookup product lowering
     "inv2_medium": lambda: inversion_case(2, "medium"),
     "inv3_low": lambda: inversion_case(3, "low", n_golden=4),
     "inv3_medium": lambda: inversion_case(3, "medium", n_golden=2),
@@ -118,7 +119,8 @@ def main():
         t0 = time.time()
         fn, inputset, ins, meta = CASES[name]()
         comp = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"} if "inv" in name else {"arrays": "encrypted", "signs": "encrypted"})
-        circuit = comp.compile(inputset, fhe.Configuration(tfhe_params="deferred"))
+        circuit = comp.compile(inputset, fhe.Configuration(
+            tfhe_params="deferred", multiplication="quarter_square" if name.endswith("quarter_square") else "auto"))
         prog = circuit.program
         expected = np.stack([np.asarray(fn(a, s)).astype(np.int64).reshape(-1) for a, s in ins])    # reference clear path
         flat_in = np.stack([np.concatenate([np.asarray(a).reshape(-1), np.asarray(s).reshape(-1)]) for a, s in ins]).astype(np.int64)

@@ -51,7 +51,22 @@ def test_comparison_family():
 
 def test_encrypted_product_is_two_lookups_each():
     c = check(lambda x, y: x * y, pairs(-3, 4, (5,)))
-    assert c.statistics["pbs"] == 10
+    assert c.statistics["pbs"] == 10                     # wide factors: quarter squares
+
+
+def test_bit_times_small_value_is_one_lookup():
+    """three quarters of the reference's lookups are digit * bit products (base_p_arrays.py:197-198, qfloat.py:892):
+    packed into one lookup by default, two with Concrete's lowering; same values"""
+    fn = lambda x, y: x * (y > 1) + (x - 1) * (1 - (y > 0))
+    inputset = [(rng.integers(0, 2, 4), rng.integers(0, 4, 4)) for _ in range(60)]
+    auto = check(fn, inputset)
+    qs = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(
+        inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, multiplication="quarter_square"))
+    assert auto.statistics["pbs"] == 4 * 4 and qs.statistics["pbs"] == 4 * 6
+    for args in inputset[:20]:
+        assert np.array_equal(auto.simulate(*args), qs.simulate(*args))
+    # one value beyond the range seen on the inputset is still handled (guard band of the packed lookup)
+    assert np.array_equal(auto.simulate(np.array([2, 0, 1, 2]), np.array([3, 3, 0, 0])), fn(np.array([2, 0, 1, 2]), np.array([3, 3, 0, 0])))
 
 
 def test_floor_div_mod_sign_abs():
