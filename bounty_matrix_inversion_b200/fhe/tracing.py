@@ -221,8 +221,11 @@ def s_mul(a, b, group=None):
         if isinstance(b, Lazy):
             return b.then(lambda x, c=a: x * c, group or Group())
         return _scale(b, a)
-    a, b = _aff(a), _aff(b)
     g = group or Group()
+    fused = _fuse_same_source(a, b, lambda u, v: u * v, g)
+    if fused is not None:
+        return fused
+    a, b = _aff(a), _aff(b)
     packed = _packed_product(a, b, g)
     if packed is not None:
         return packed
@@ -230,6 +233,26 @@ def s_mul(a, b, group=None):
     plus = Lazy(_lin(a, b, 1), _sq4, g.child("sum")).aff()
     minus = Lazy(_lin(a, b, -1), _sq4, g.child("difference")).aff()
     return _lin(plus, minus, -1)
+
+
+def _same_form(x: Aff, y: Aff) -> bool:
+    return x is y or (x.const == y.const and x.terms == y.terms)
+
+
+def _fuse_same_source(a, b, op, g: Group):
+    """op(a, b) when both operands are functions of ONE affine form (two pending lookups on the same input, or a
+    pending lookup and its own input): still a univariate function, so one lookup -- what Concrete's fusing does with
+    `(np.abs(curr) // base) * np.sign(curr)` (qfloat.py:619) or `array * (array >= 0)` (qfloat.py:663)."""
+    ident = lambda x: x
+    if isinstance(a, Lazy) and isinstance(b, Lazy) and _same_form(a.src, b.src):
+        src, fa, fb = a.src, a.fn, b.fn
+    elif isinstance(a, Lazy) and isinstance(b, Aff) and _same_form(a.src, b):
+        src, fa, fb = a.src, a.fn, ident
+    elif isinstance(b, Lazy) and isinstance(a, Aff) and _same_form(b.src, a):
+        src, fa, fb = b.src, ident, b.fn
+    else:
+        return None
+    return Lazy(src, lambda x, fa=fa, fb=fb: op(np.asarray(fa(x)), np.asarray(fb(x))), g)
 
 
 _PACK_SPAN = 8      # packed products stay within 3 message bits, below every circuit's width
@@ -278,6 +301,9 @@ def s_compare(a, b, op, group=None):
         return s_univariate(a, lambda x, c=b: op(x, c).astype(np.int64), group)
     if isinstance(a, int):
         return s_univariate(b, lambda x, c=a: op(c, x).astype(np.int64), group)
+    fused = _fuse_same_source(a, b, lambda u, v: op(u, v).astype(np.int64), group or Group())
+    if fused is not None:
+        return fused
     return s_univariate(_lin(_aff(a), _aff(b), -1), lambda x: op(x, 0).astype(np.int64), group)
 
 
@@ -293,6 +319,9 @@ def s_bitwise(a, b, op, group=None):
         return s_univariate(a, lambda x, c=b: op(x, c), group)
     if isinstance(a, int):
         return s_univariate(b, lambda x, c=a: op(c, x), group)
+    fused = _fuse_same_source(a, b, lambda u, v: op(u, v), group or Group())
+    if fused is not None:
+        return fused
     if min(a.vals.min(), b.vals.min()) < 0:
         raise NotImplementedError("bitwise operations between signed encrypted values")
     sh = _bits(b.vals.max())        # pack both operands into one lookup input, as Concrete's chunked bitwise does

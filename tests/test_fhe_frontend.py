@@ -178,3 +178,12 @@ def test_non_strict_evaluation_flags_out_of_range_lanes():
     assert list(bad) == [False, True] and np.array_equal(out[0], [3, 3])
     with pytest.raises(OverflowError):
         c.program.evaluate_clear(outside[0])
+
+
+def test_functions_of_the_same_input_fuse_across_a_product():
+    """(abs(c) // 2) * sign(c) and c * (c >= 0) are univariate in c: one lookup each (qfloat.py:619, 663)"""
+    def fn(x, y):
+        c = x - y
+        return np.concatenate(((np.abs(c) // 2) * np.sign(c), c * (c >= 0), (c > 0) & (c < 3)), axis=0)
+    c = check(fn, pairs(-4, 5, (3,)))
+    assert c.statistics["pbs"] == 9 and c.statistics["levels"] == 1
