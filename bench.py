@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--pairs", type=int, default=24, help="QFloat pairs (batch lanes) per step and per GPU")
+    ap.add_argument("--pairs", type=int, default=48, help="QFloat pairs (batch lanes) per step and per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inversion", default="", help="also time one encrypted inversion: 2 | 3 | 4 (low precision) or a "
