@@ -98,6 +98,8 @@ class Executor:
         if self.world > 1:
             rows = shard_bounds(self.max_pbs, 0, self.world)[0] * self.world       # padded so every rank owns `per` rows
             self.stage = torch.empty((rows, batch, self.W1), dtype=torch.int64, device=self.dev)
+            self.mine = torch.empty((rows // self.world, batch, self.W1), dtype=torch.int64, device=self.dev)
+            self.iota = torch.arange(rows, dtype=torch.int32, device=self.dev)
         self._batch = batch
 
     def run(self, input_cts: np.ndarray) -> np.ndarray:
@@ -167,8 +169,8 @@ class Executor:
         eng.keyswitch(self.ks_in, self.small, n_ks * batch, stream=st)
         stage = self.stage[: per * self.world]
         if hi > lo:
-            local_out = torch.arange(lo, hi, dtype=torch.int32, device=self.dev)
-            eng.pbs(self.small, job_ks[lo:hi], job_lut[lo:hi], local_out, stage, hi - lo, batch, stream=st)
+            eng.pbs(self.small, job_ks[lo:hi], job_lut[lo:hi], self.iota[lo:hi], stage, hi - lo, batch, stream=st)
         mine = stage[self.rank * per: (self.rank + 1) * per]
-        dist.all_gather_into_tensor(stage, mine.clone(), group=self.group)
+        self.mine[:per].copy_(mine)                       # all_gather needs an input that does not alias the output
+        dist.all_gather_into_tensor(stage, self.mine[:per], group=self.group)
         self.vals.index_copy_(0, job_out.long(), stage[:n_pbs])

@@ -65,3 +65,27 @@ def test_compile_and_run_small_function(native):
     circuit = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
     for x, y in inputset[:5]:
         assert np.array_equal(circuit.encrypt_run_decrypt(x, y), fn(x, y))
+
+
+def test_purely_leveled_circuit_needs_no_bootstrap(native):
+    """edge case: a circuit without table lookups is one lincomb launch (no keyswitch, no PBS)"""
+    rng = np.random.default_rng(2)
+    fn = lambda x, y: 3 * x - y + np.sum(y) - 2
+    inputset = [(rng.integers(-3, 4, 4), rng.integers(-3, 4, 4)) for _ in range(30)]
+    circuit = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
+    assert circuit.statistics["pbs"] == 0
+    for x, y in inputset[:4]:
+        assert np.array_equal(circuit.encrypt_run_decrypt(x, y), fn(x, y))
+
+
+def test_ragged_batch_and_every_kernel_build(native):
+    """5 lanes (not a multiple of the keyswitch tile) through the automatic, latency, throughput and 8-CTA builds"""
+    prog, x, want = load("qf_sub_medium")
+    circuit = fhe.Circuit.from_program(prog, PR.TOY_1024_L1)
+    enc = circuit.encrypt_batch([(row,) for row in x[:5]])
+    ex = circuit.executor()
+    for mode in (0, 1, 2, 3):
+        ex.eng.set_pbs_mode(mode)
+        got = circuit.decrypt(circuit.run(enc))
+        assert np.array_equal(np.stack(got), want[:5]), mode
+    ex.eng.set_pbs_mode(0)
