@@ -8,7 +8,7 @@
  *   ------------------------------------------------------------  --------------------------
  *   circuit.keygen()            main.py:177                       bmi_keygen_*
  *   circuit.encrypt(x, y)       qfloat_matrix_inversion.py:1032   bmi_lwe_encrypt
- *   circuit.run(encrypted)      qfloat_matrix_inversion.py:1034   bmi_program_run / bmi_level_*
+ *   circuit.run(encrypted)      qfloat_matrix_inversion.py:1034   one bmi_lincomb + bmi_keyswitch + bmi_pbs per level
  *     every table lookup (%, //, <, abs, sign, enc*enc ...)       bmi_keyswitch + bmi_pbs
  *       base_p_arrays.py:102-103,122,197-198  qfloat.py:619,663-670
  *     every leveled add / sub / scalar multiply                   bmi_lincomb
