@@ -16,7 +16,8 @@ from .program import Program, lower
 class Configuration:
     """accepts Concrete's keyword options; the ones this engine understands:
     tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, seed, device,
-    multiplication ("auto" | "quarter_square", see tracing.Trace)"""
+    multiplication ("auto" | "quarter_square", see tracing.Trace),
+    split_wide ("auto" | True | False) and split_guard (see program.lower)"""
 
     def __init__(self, **options):
         self.options = dict(options)
@@ -26,6 +27,8 @@ class Configuration:
         self.seed = options.get("seed", 0x5EED)
         self.device = options.get("device", 0)
         self.multiplication = options.get("multiplication", "auto")
+        self.split_wide = options.get("split_wide", "auto")
+        self.split_guard = options.get("split_guard")
 
     def fork(self, **options):
         merged = dict(self.options)
@@ -92,7 +95,8 @@ class Compiler:
         trace, flat_out, out_shapes, in_shapes = self.trace(inputset, cfg.multiplication)
         t1 = time.time()
         n_out = len(flat_out)
-        prog = lower(trace, flat_out, (n_out,), slack_bits=cfg.slack_bits)
+        prog = lower(trace, flat_out, (n_out,), slack_bits=cfg.slack_bits, split_wide=cfg.split_wide,
+                     split_guard=cfg.split_guard)
         t2 = time.time()
         prm = None if cfg.tfhe_params == "deferred" else (cfg.tfhe_params or PR.for_width(prog.width, prog.nu2))
         prog.stats.update(trace_s=round(t1 - t0, 3), lower_s=round(t2 - t1, 3), params_s=round(time.time() - t2, 3))

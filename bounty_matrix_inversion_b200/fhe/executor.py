@@ -37,8 +37,10 @@ class Executor:
         self.rank, self.world, self.group = rank, world, group
         W1 = getattr(engine, "words", params.big_dim + 1)
         self.W1 = W1
-        engine.load_luts(program.lut_polynomials(params.N) if not getattr(engine, "clear", False) else program.tables)
-        scale = PR.delta(program.width) if not getattr(engine, "clear", False) else 1
+        # a clear-text stand-in engine computes in half-message units (Program.tables_half_units)
+        clear = getattr(engine, "clear", False)
+        engine.load_luts(program.tables_half_units() if clear else program.lut_polynomials(params.N))
+        scale = 2 if clear else PR.delta(program.width)
         lv = program.levels
 
         def cat(arrs, dtype):

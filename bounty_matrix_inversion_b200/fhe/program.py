@@ -10,6 +10,17 @@ whose input ranges over [lo, hi] on the inputset reads the table at (value + off
 range centred in [0, 2^W).  W is the smallest width that fits every lookup input range, the
 quantity Concrete's bit-width assignment derives from the same inputset
 (/root/reference/matrix_inversion/qfloat_matrix_inversion.py:981-1004).
+
+Wide-lookup splitting.  The polynomial size (hence the cost of EVERY bootstrap) follows W, yet in the
+reference's circuits a handful of lookups are one bit wider than all the others (22 of 29 k in the 3x3
+inversion).  Such a lookup F on y in [0, 2^(W+1)) is lowered to three W-bit bootstraps that use the
+padding bit and the negacyclic wrap T(y + 2^W) = -T(y) of the accumulator:
+    s  = PBS_const(y)            = +2^(W-1) for y < 2^W, -2^(W-1) above           (the sign, for free)
+    y' = y - 2^(W-1) + s         = y mod 2^W                                       (leveled)
+    F(y) = PBS_A(y) + PBS_G(y'),   A(t) = (F(t) - F(t + 2^W)) / 2,  G(t) = (F(t) + F(t + 2^W)) / 2
+A and G may be half-integers; accumulator entries are arbitrary torus elements, so those tables are stored
+doubled and encoded at half the plaintext scale (`table_half`); their sum is always an integer message.
+Keyswitch rows that legitimately use the padding bit are flagged `Level.full`.
 """
 from __future__ import annotations
 
@@ -30,6 +41,11 @@ class Level:
     job_ks: np.ndarray       # [n_pbs] int32 row of this level's keyswitch batch
     job_lut: np.ndarray      # [n_pbs] int32
     job_out: np.ndarray      # [n_pbs] int32 value slot
+    full: np.ndarray = None  # [n_ks] bool: row ranges over the whole torus (padding bit used on purpose)
+
+    def __post_init__(self):
+        if self.full is None:
+            self.full = np.zeros(len(self.konst), bool)
 
 
 @dataclass
@@ -47,6 +63,11 @@ class Program:
     tables: np.ndarray       # [n_luts][2^W] int64 table outputs (message units)
     nu2: int                 # largest squared 2-norm of a lookup input's linear combination
     stats: dict = field(default_factory=dict)
+    table_half: np.ndarray = None   # [n_luts] bool: table holds 2x its values (half-integer outputs)
+
+    def __post_init__(self):
+        if self.table_half is None:
+            self.table_half = np.zeros(len(self.tables), bool)
 
     @property
     def n_pbs(self):
@@ -58,7 +79,12 @@ class Program:
 
     def lut_polynomials(self, N: int) -> np.ndarray:
         W = self.width
-        return np.stack([PR.lut_polynomial([PR.encode(int(t), W) for t in tab], W, N) for tab in self.tables])
+        return np.stack([PR.lut_polynomial([PR.encode(int(t), W + int(h)) for t in tab], W, N)
+                         for tab, h in zip(self.tables, self.table_half)])
+
+    def tables_half_units(self) -> np.ndarray:
+        """every table in units of half a message (what evaluate_clear and clear-text stand-in engines compute in)"""
+        return self.tables * np.where(self.table_half, 1, 2)[:, None]
 
     # ------------------------------------------------------------ (de)serialisation
     def save(self, path, **extra):
@@ -74,7 +100,8 @@ class Program:
             job_ks=cat([l.job_ks for l in lv], np.int32), job_lut=cat([l.job_lut for l in lv], np.int16),
             job_out=cat([l.job_out for l in lv], np.int32), out_row_ptr=self.out_row_ptr, out_idx=self.out_idx,
             out_coef=self.out_coef, out_konst=self.out_konst, out_shape=np.array(self.out_shape, np.int64),
-            tables=self.tables.astype(np.int16 if self.width < 15 else np.int64), nu2=self.nu2,
+            tables=self.tables.astype(np.int16 if self.width < 14 else np.int64), nu2=self.nu2,
+            table_half=self.table_half, ks_full=cat([l.full for l in lv], bool),
             stats=np.array(repr(self.stats)), **extra)
 
     @classmethod
@@ -87,15 +114,17 @@ class Program:
         row_ptr, idx, coef, konst = (z["row_ptr"].astype(np.int32), z["idx"].astype(np.int32), z["coef"].astype(np.int64),
                                      z["konst"].astype(np.int64))
         job_ks, job_lut, job_out = z["job_ks"].astype(np.int32), z["job_lut"].astype(np.int32), z["job_out"].astype(np.int32)
+        full = z["ks_full"].astype(bool) if "ks_full" in z else np.zeros(len(konst), bool)
         levels = []
         for i in range(len(ks)):
             levels.append(Level(row_ptr[ro[i]:ro[i + 1]], idx[no[i]:no[i + 1]], coef[no[i]:no[i + 1]], konst[ko[i]:ko[i + 1]],
-                                job_ks[po[i]:po[i + 1]], job_lut[po[i]:po[i + 1]], job_out[po[i]:po[i + 1]]))
+                                job_ks[po[i]:po[i + 1]], job_lut[po[i]:po[i + 1]], job_out[po[i]:po[i + 1]],
+                                full[ko[i]:ko[i + 1]]))
         import ast
         prog = cls(int(z["width"]), int(z["n_inputs"]), int(z["n_slots"]), z["input_slots"].astype(np.int32), levels,
                    z["out_row_ptr"].astype(np.int32), z["out_idx"].astype(np.int32), z["out_coef"].astype(np.int64),
                    z["out_konst"].astype(np.int64), tuple(int(v) for v in z["out_shape"]), z["tables"].astype(np.int64),
-                   int(z["nu2"]))
+                   int(z["nu2"]), table_half=z["table_half"].astype(bool) if "table_half" in z else None)
         prog.stats = ast.literal_eval(str(z["stats"]))
         return prog
 
@@ -110,28 +139,42 @@ class Program:
         single = x.ndim == 1
         x = np.atleast_2d(x)
         B, W = x.shape[0], self.width
-        vals = np.zeros((self.n_slots, B), np.int64)
-        vals[self.input_slots] = x.T
+        size = 1 << W
+        tab2 = self.tables_half_units()
+        vals = np.zeros((self.n_slots, B), np.int64)          # half-message units throughout
+        vals[self.input_slots] = 2 * x.T
         bad = np.zeros(B, bool)
         for lv in self.levels:
-            ks = _csr_apply(lv.row_ptr, lv.idx, lv.coef, lv.konst, vals)
-            if ks.size and (ks.min() < 0 or ks.max() >= (1 << W)):
+            ks2 = _csr_apply(lv.row_ptr, lv.idx, lv.coef, 2 * lv.konst, vals)
+            assert not (ks2 & 1).any(), "half-integer lookup input: split tables combined with unequal coefficients"
+            ks = ks2 >> 1
+            # what the bootstrap sees: the message mod 2^(W+1) (table outputs are stored reduced, so only the residue
+            # is meaningful); the upper half is the padding bit -- out of range unless the row uses it on purpose --
+            # and reads the negated table (negacyclic)
+            m = np.mod(ks, 2 * size)
+            neg = m >= size
+            oob = neg & ~lv.full[:, None]
+            if oob.any():
                 if strict:
-                    raise OverflowError(f"lookup input outside the {W}-bit message space: [{ks.min()}, {ks.max()}]")
-                oob = (ks < 0) | (ks >= (1 << W))
+                    raise OverflowError(f"lookup input outside the {W}-bit message space: {np.unique(m[oob] - 2 * size)[:8]}")
                 bad |= oob.any(axis=0)
-                # what the bootstrap does: message mod 2^(W+1); upper half reads the negated table (negacyclic)
-                m = np.mod(ks, 1 << (W + 1))
-                neg = m >= (1 << W)
-                t = self.tables[lv.job_lut[:, None], np.where(neg, m - (1 << W), m)[lv.job_ks]]
-                vals[lv.job_out] = np.where(neg[lv.job_ks], -t, t)
-                continue
-            vals[lv.job_out] = self.tables[lv.job_lut[:, None], ks[lv.job_ks]]
-        out = _csr_apply(self.out_row_ptr, self.out_idx, self.out_coef, self.out_konst, vals)
-        out = out.T.reshape((B,) + tuple(self.out_shape))
+            t = tab2[lv.job_lut[:, None], np.where(neg, m - size, m)[lv.job_ks]]
+            vals[lv.job_out] = np.where(neg[lv.job_ks], -t, t)
+        out2 = _csr_apply(self.out_row_ptr, self.out_idx, self.out_coef, 2 * self.out_konst, vals)
+        assert not (out2 & 1).any()
+        out = (np.mod((out2 >> 1) + size, 2 * size) - size).T.reshape((B,) + tuple(self.out_shape))
         if strict:
             return out[0] if single else out
         return (out[0], bad[0]) if single else (out, bad)
+
+
+def _narrowing_pays(wide: "Program", narrow: "Program") -> bool:
+    """one bit of width doubles the polynomial size: bootstrap work grows 2 (W + 7) / (W + 6)-fold (transform
+    butterflies), the latency of one level about 1.6-fold (measured)"""
+    W = wide.width
+    work = lambda p, w: p.n_pbs * (1 << w) * (w + 7)
+    path = lambda p, w: len(p.levels) * 1.6 ** w
+    return work(narrow, W - 1) < work(wide, W) and path(narrow, W - 1) < 1.1 * path(wide, W)
 
 
 def _csr_apply(row_ptr, idx, coef, konst, vals):
@@ -144,9 +187,20 @@ def _csr_apply(row_ptr, idx, coef, konst, vals):
 
 
 # ------------------------------------------------------------------ lowering
-def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1) -> Program:
+def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, split_wide="auto", split_guard=None) -> Program:
     """trace: fhe.tracing.Trace after the circuit function ran; outputs: flat list of scalars
-    (ints / Aff) the function returned"""
+    (ints / Aff) the function returned.
+    split_wide: True lowers the lookups that alone need the top bit of width into three narrower bootstraps (module
+    docstring); False never does; "auto" does when the narrower width halves the polynomial size (W >= 5), the wide
+    lookups are a minority, and the narrowed program is cheaper both in total bootstrap work and along its critical
+    path (`_narrowing_pays`).  split_guard: spare table entries required either side of a lookup's observed range in a narrowed
+    program, lookups with less are split as well (default 2^W / 4)."""
+    if split_wide == "auto":
+        wide = lower(trace, outputs, out_shape, slack_bits, min_width, False)
+        if wide.width - slack_bits < 5 or wide.stats["top_width_lookups"] * 10 > wide.stats["live_lookups"]:
+            return wide
+        narrow = lower(trace, outputs, out_shape, slack_bits, min_width, True, split_guard)
+        return narrow if narrow.width < wide.width and _narrowing_pays(wide, narrow) else wide
     n_in = trace.n_inputs
     jobs = trace.jobs
 
@@ -164,58 +218,96 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1) ->
         live[j] = True
         stack.extend(t for t in jobs[j].terms if t >= n_in)
 
-    # --- message width: every live lookup's input range must fit
-    W = min_width
-    for j in np.flatnonzero(live):
-        g = jobs[j].group
-        W = max(W, int(g.hi - g.lo).bit_length())
+    # --- message width: every live lookup's input range must fit (or be split), every output value too
+    bits = {int(j): int(jobs[j].group.hi - jobs[j].group.lo).bit_length() for j in np.flatnonzero(live)}
+    W_out = min_width
     for o in outputs:
         if not isinstance(o, int):
-            W = max(W, int(max(abs(int(o.vals.min())), abs(int(o.vals.max())))).bit_length())
+            W_out = max(W_out, int(max(abs(int(o.vals.min())), abs(int(o.vals.max())))).bit_length())
+    W = max([W_out] + list(bits.values()))
+    n_top = sum(1 for v in bits.values() if v == W)
+    narrowed = False
+    if split_wide and W > max(W_out, 1) and n_top:
+        W -= 1
+        narrowed = True
     W += slack_bits
     size = 1 << W
     dom = np.arange(size, dtype=np.int64)
+    # a narrowed program keeps spare table entries either side of every observed range (else the lookup is split too):
+    # unseen inputs stray a little outside the inputset's ranges, which the wider program absorbed for free
+    guard = (size // 4 if narrowed else 0) if split_guard is None else int(split_guard)
 
     # --- tables, common-subexpression elimination of lookups and of keyswitches
-    table_ids, tables = {}, []
+    table_ids, tables, table_half = {}, [], []
     lookup_ids = {}            # (src key, table id) -> representative base
-    alias = {}                 # base -> representative base
-    job_info = {}              # representative base -> (src key, offset, table id)
-    nu2 = 1
+    subst = {}                 # traced base -> {representative base: coefficient} where they differ
+    job_info = {}              # representative base -> (src key, table id)
+    full_keys = set()          # keyswitch rows that use the padding bit on purpose
+    state = {"nu2": 1, "next": n_in + len(jobs), "split": 0}
 
-    def resolve(b):
-        return alias.get(b, b)
-
-    for j in np.flatnonzero(live):        # jobs are in creation (topological) order
-        jb = jobs[j]
-        g = jb.group
-        offset = (size - (g.hi - g.lo + 1)) // 2 - g.lo           # centre [lo, hi] in [0, 2^W)
+    def resolve(src):
         terms = {}
-        for b, c in jb.terms.items():
-            rb = resolve(b)
-            v = terms.get(rb, 0) + c
-            if v:
-                terms[rb] = v
-            else:
-                terms.pop(rb, None)
-        key = (tuple(sorted(terms.items())), jb.const + offset)
-        tab = np.asarray(jb.fn(dom - offset), dtype=np.int64)
+        for b, c in src.items():
+            for rb, rc in (subst[b].items() if b in subst else ((b, 1),)):
+                v = terms.get(rb, 0) + c * rc
+                if v:
+                    terms[rb] = v
+                else:
+                    terms.pop(rb, None)
+        return terms
+
+    def add_lookup(base, key, tab, half=False):
+        """registers lookup `tab` of keyswitch row `key`; returns the base that holds its result"""
+        tab = np.asarray(tab, dtype=np.int64)
         if tab.shape != (size,):
             tab = np.broadcast_to(tab, (size,)).copy()
         # entries for inputs never seen on the inputset may be anything; arithmetic is mod 2^(W+1) anyway
-        tab = ((tab + size) % (2 * size)) - size
-        h = hashlib.blake2b(tab.tobytes(), digest_size=16).digest()
+        span = 4 * size if half else 2 * size
+        tab = ((tab + span // 2) % span) - span // 2
+        h = hashlib.blake2b(tab.tobytes() + bytes([half]), digest_size=16).digest()
         tid = table_ids.get(h)
         if tid is None:
             tid = table_ids[h] = len(tables)
             tables.append(tab)
+            table_half.append(half)
         rep = lookup_ids.get((key, tid))
         if rep is not None:
-            alias[jb.base] = rep
+            return rep
+        if base is None:
+            base = state["next"]
+            state["next"] += 1
+        lookup_ids[(key, tid)] = base
+        job_info[base] = (key, tid)
+        state["nu2"] = max(state["nu2"], sum(c * c for _b, c in key[0]))
+        return base
+
+    for j in np.flatnonzero(live):        # jobs are in creation (topological) order
+        jb = jobs[j]
+        g = jb.group
+        terms = resolve(jb.terms)
+        if (g.hi - g.lo + 1) + 2 * guard <= size or not narrowed:
+            offset = (size - (g.hi - g.lo + 1)) // 2 - g.lo           # centre [lo, hi] in [0, 2^W)
+            key = (tuple(sorted(terms.items())), jb.const + offset)
+            rep = add_lookup(jb.base, key, jb.fn(dom - offset))
+            if rep != jb.base:
+                subst[jb.base] = {rep: 1}
             continue
-        lookup_ids[(key, tid)] = jb.base
-        job_info[jb.base] = (key, tid)
-        nu2 = max(nu2, sum(c * c for c in terms.values()))
+        # one bit too wide: sign through the padding bit, then negacyclic + cyclic halves (module docstring)
+        assert bits[int(j)] <= W + 1, "lookup more than one bit wider than the program width"
+        offset = (2 * size - (g.hi - g.lo + 1)) // 2 - g.lo           # centre [lo, hi] in [0, 2^(W+1))
+        f = np.asarray(jb.fn(np.arange(2 * size, dtype=np.int64) - offset), dtype=np.int64)
+        f = np.broadcast_to(f, (2 * size,))
+        key_y = (tuple(sorted(terms.items())), jb.const + offset)
+        full_keys.add(key_y)
+        sgn = add_lookup(None, key_y, np.full(size, size // 2))
+        neg = add_lookup(None, key_y, f[:size] - f[size:], half=True)
+        low = dict(terms)
+        low[sgn] = low.get(sgn, 0) + 1
+        key_low = (tuple(sorted(low.items())), jb.const + offset - size // 2)
+        cyc = add_lookup(None, key_low, f[:size] + f[size:], half=True)
+        subst[jb.base] = {neg: 1, cyc: 1}
+        state["split"] += 1
+    nu2 = state["nu2"]
 
     # --- levels (as soon as possible)
     level_of = {}
@@ -233,18 +325,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1) ->
     # --- outputs as linear combinations of representatives
     out_rows = []
     for o in outputs:
-        if isinstance(o, int):
-            out_rows.append(({}, o))
-            continue
-        terms = {}
-        for b, c in o.terms.items():
-            rb = resolve(b)
-            v = terms.get(rb, 0) + c
-            if v:
-                terms[rb] = v
-            else:
-                terms.pop(rb, None)
-        out_rows.append((terms, o.const))
+        out_rows.append(({}, o) if isinstance(o, int) else (resolve(o.terms), o.const))
 
     # --- liveness -> slot reuse
     last_use = {b: 0 for b in range(n_in)}
@@ -291,7 +372,8 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1) ->
             row_ptr[r + 1] = len(idx)
             konst.append(k)
         levels.append(Level(row_ptr, np.asarray(idx, np.int32), np.asarray(coef, np.int64), np.asarray(konst, np.int64),
-                            np.asarray(job_ks, np.int32), np.asarray(job_lut, np.int32), np.asarray(job_out, np.int32)))
+                            np.asarray(job_ks, np.int32), np.asarray(job_lut, np.int32), np.asarray(job_out, np.int32),
+                            np.array([key in full_keys for key in ks_rows], bool)))
         for b in expiring[li]:              # values last read at this level free their slot for the next one
             free.append(slot_of[b])
 
@@ -306,8 +388,9 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1) ->
 
     prog = Program(W, n_in, n_slots, np.arange(n_in, dtype=np.int32), levels, out_ptr, np.asarray(oidx, np.int32),
                    np.asarray(ocoef, np.int64), np.asarray(okonst, np.int64), tuple(out_shape),
-                   np.stack(tables) if tables else np.zeros((1, size), np.int64), int(nu2))
+                   np.stack(tables) if tables else np.zeros((1, size), np.int64), int(nu2),
+                   table_half=np.asarray(table_half, bool) if tables else None)
     prog.stats = {"traced_lookups": len(jobs), "live_lookups": int(live.sum()), "pbs": prog.n_pbs, "keyswitches": prog.n_ks,
                   "levels": n_levels, "tables": len(tables), "slots": n_slots, "width": W, "nu2": int(nu2),
-                  "max_level_pbs": max((len(l.job_ks) for l in levels), default=0)}
+                  "max_level_pbs": max((len(l.job_ks) for l in levels), default=0), "split_lookups": state["split"], "top_width_lookups": n_top}
     return prog

@@ -8,8 +8,9 @@ from bounty_matrix_inversion_b200 import fhe, params as PR
 rng = np.random.default_rng(7)
 
 
-def compile_(fn, inputset, names=("x", "y")):
-    return fhe.Compiler(fn, {n: "encrypted" for n in names}).compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
+def compile_(fn, inputset, names=("x", "y"), **options):
+    return fhe.Compiler(fn, {n: "encrypted" for n in names}).compile(
+        inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, **options))
 
 
 def pairs(lo, hi, shape, count=60):
@@ -143,7 +144,7 @@ def test_errors():
 
 def test_width_and_norm_drive_parameter_choice():
     extremes = [(np.zeros(8, np.int64), np.zeros(8, np.int64)), (np.ones(8, np.int64), np.ones(8, np.int64))]
-    c = compile_(lambda x, y: (np.sum(x) + np.sum(y)) // 4, pairs(0, 2, (8,)) + extremes)
+    c = compile_(lambda x, y: (np.sum(x) + np.sum(y)) // 4, pairs(0, 2, (8,)) + extremes, split_wide=False)
     assert c.program.width == 5 and c.program.nu2 == 16            # values 0..16 need 17 table entries
     p = PR.optimize(3, 4)
     assert p.k == 1 and PR.failure_sigmas(p, 3, 4) >= 6.5 and p.N >= 1024
@@ -187,3 +188,59 @@ def test_functions_of_the_same_input_fuse_across_a_product():
         return np.concatenate(((np.abs(c) // 2) * np.sign(c), c * (c >= 0), (c > 0) & (c < 3)), axis=0)
     c = check(fn, pairs(-4, 5, (3,)))
     assert c.statistics["pbs"] == 9 and c.statistics["levels"] == 1
+
+
+# ---------------------------------------------------------------- wide-lookup splitting (program.lower docstring)
+def _wide_circuit(x, y):
+    s = np.sum(x) + np.sum(y)                    # 0..16: one value more than 4 bits hold
+    out = fhe.zeros(3)
+    out[0], out[1], out[2] = s // 3, fhe.univariate(lambda v: (v * v) % 7 - 3)(s), s % 2
+    return out + x[:3] % 2
+
+
+def test_wide_lookup_is_split_into_three_narrow_ones():
+    extremes = [(np.zeros(8, np.int64), np.zeros(8, np.int64)), (np.ones(8, np.int64), np.ones(8, np.int64))]
+    inputset = pairs(0, 2, (8,)) + extremes
+    wide = compile_(_wide_circuit, inputset, split_wide=False)
+    split = compile_(_wide_circuit, inputset, split_wide=True, split_guard=0)
+    auto = compile_(_wide_circuit, inputset)
+    assert wide.program.width == 5 and split.program.width == 4
+    assert auto.program.width == 5 and auto.statistics["split_lookups"] == 0        # 3 of 6 lookups are wide: not worth it
+    st = split.statistics
+    # three wide lookups of one source: ONE shared sign bootstrap, one negacyclic + one cyclic half each
+    assert st["split_lookups"] == 3 and st["pbs"] == wide.statistics["pbs"] + 3 + 1 and st["levels"] == 2
+    assert split.program.table_half.sum() >= 2 and sum(int(l.full.sum()) for l in split.program.levels) == 1
+    for args in inputset:
+        want = _wide_circuit(*args)
+        assert np.array_equal(split.simulate(*args), want) and np.array_equal(wide.simulate(*args), want)
+    # every value of the 17-entry range, both sides of the padding bit
+    for total in range(17):
+        x = np.array([1] * min(total, 8) + [0] * (8 - min(total, 8)))
+        y = np.array([1] * max(total - 8, 0) + [0] * (8 - max(total - 8, 0)))
+        assert np.array_equal(split.simulate(x, y), _wide_circuit(x, y)), total
+
+
+def test_split_program_round_trips_through_npz(tmp_path):
+    extremes = [(np.zeros(8, np.int64), np.zeros(8, np.int64)), (np.ones(8, np.int64), np.ones(8, np.int64))]
+    c = compile_(_wide_circuit, pairs(0, 2, (8,)) + extremes, split_wide=True)
+    path = str(tmp_path / "p.npz")
+    c.program.save(path)
+    from bounty_matrix_inversion_b200.fhe.program import Program
+    q = Program.load(path)
+    assert np.array_equal(q.table_half, c.program.table_half) and np.array_equal(q.tables, c.program.tables)
+    assert all(np.array_equal(a.full, b.full) for a, b in zip(q.levels, c.program.levels))
+    x = np.ones((5, 16), np.int64)
+    assert np.array_equal(q.evaluate_clear(x), c.program.evaluate_clear(x))
+    # the accumulators of half-unit tables carry odd multiples of half the plaintext scale
+    polys = q.lut_polynomials(1024)
+    half_scale = PR.delta(q.width) // 2
+    odd = [(int(v) if int(v) < PR.P // 2 else int(v) - PR.P) // half_scale % 2 for v in polys[q.table_half].reshape(-1)[::32]]
+    assert any(odd) or not (q.tables[q.table_half] % 2).any()
+
+
+def test_split_overflow_is_still_detected():
+    extremes = [(np.zeros(8, np.int64), np.zeros(8, np.int64)), (np.ones(8, np.int64), np.ones(8, np.int64))]
+    c = compile_(_wide_circuit, pairs(0, 2, (8,)) + extremes, split_wide=True)
+    # the split lookup itself accepts the whole torus; a narrow one (x % 2, inputs 0..1) still reports leaving its range
+    with pytest.raises(OverflowError):
+        c.program.evaluate_clear(np.array([12] + [0] * 15, np.int64))

@@ -84,3 +84,36 @@ def test_encrypted_execution_on_the_oracle(oracle):
     out = run_program_oracle(oracle, prog, prm, keys.bsk, keys.ksk, cts)
     dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
     assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[0])
+
+
+def wide_sum_circuit():
+    """a circuit whose one wide lookup source (sum of 16 bits: 17 values) is lowered to sign + two half-unit tables"""
+    from bounty_matrix_inversion_b200 import fhe
+    rng = np.random.default_rng(11)
+
+    def fn(x, y):
+        s = np.sum(x) + np.sum(y)
+        out = fhe.zeros(3)
+        out[0], out[1], out[2] = s // 3, fhe.univariate(lambda v: (v * v) % 7 - 3)(s), s % 2
+        return out + x[:3] % 2
+
+    inputset = [(rng.integers(0, 2, 8), rng.integers(0, 2, 8)) for _ in range(40)]
+    inputset += [(np.zeros(8, np.int64), np.zeros(8, np.int64)), (np.ones(8, np.int64), np.ones(8, np.int64))]
+    circuit = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(
+        inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, split_wide=True, split_guard=0))
+    return fn, inputset, circuit
+
+
+def test_split_wide_lookup_under_encryption_on_the_oracle(oracle):
+    """padding-bit sign bootstrap and half-scale accumulators at the ciphertext level (program.lower docstring)"""
+    from oracle_exec import run_program_oracle
+    fn, inputset, circuit = wide_sum_circuit()
+    prog, prm = circuit.program, PR.TOY_1024
+    assert prog.width == 4 and prog.stats["split_lookups"] == 3 and prog.table_half.any()
+    keys = oracle.Keys(prm, seed=5)
+    for x, y in (inputset[0], inputset[-1], inputset[-2], inputset[3]):        # includes sums 0 and 16
+        flat = np.concatenate([x, y])
+        cts = np.stack([oracle.encrypt_big(prm, keys.S, 5, i, PR.encode(int(m), prog.width)) for i, m in enumerate(flat)])
+        out = run_program_oracle(oracle, prog, prm, keys.bsk, keys.ksk, cts)
+        dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
+        assert np.array_equal(dec, fn(x, y)), (x, y)

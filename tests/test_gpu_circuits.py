@@ -89,3 +89,20 @@ def test_ragged_batch_and_every_kernel_build(native):
         got = circuit.decrypt(circuit.run(enc))
         assert np.array_equal(np.stack(got), want[:5]), mode
     ex.eng.set_pbs_mode(0)
+
+
+def test_split_wide_lookup_matches_oracle_and_clear_path(native, oracle):
+    """lookup one bit wider than the program: sign through the padding bit + negacyclic and cyclic half tables"""
+    from oracle_exec import run_program_oracle
+    from test_golden_programs import wide_sum_circuit
+    fn, inputset, circuit = wide_sum_circuit()
+    prm = PR.TOY_1024
+    for x, y in (inputset[0], inputset[-1], inputset[-2]):
+        enc = circuit.encrypt(x, y)
+        out = circuit.run(enc)
+        assert np.array_equal(circuit.decrypt(out), fn(x, y))
+    ref = run_program_oracle(oracle, circuit.program, prm, circuit.keys.bsk, circuit.keys.ksk, enc.cts)
+    assert np.array_equal(out.cts, ref)
+    lanes = inputset[:9]
+    got = circuit.decrypt(circuit.run(circuit.encrypt_batch(lanes)))
+    assert np.array_equal(np.stack(got), np.stack([fn(x, y) for x, y in lanes]))

@@ -19,8 +19,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 class ClearEngine:
-    """same call surface as native.Engine, operating on clear messages (1 word per ciphertext)"""
+    """same call surface as native.Engine, operating on clear messages in half-message units (1 word per ciphertext)"""
     clear, words, small_words = True, 1, 1
+
+    def __init__(self, width):
+        self.size = 1 << width
 
     def load_luts(self, tables):
         self.tables = torch.from_numpy(np.asarray(tables, dtype=np.int64))
@@ -42,7 +45,15 @@ class ClearEngine:
     def pbs(self, small, job_in, job_lut, job_out, out, njobs, batch=1, stream=None):
         s, o = small.view(-1, batch, 1), out.view(-1, batch, 1)
         for q in range(njobs):
-            o[job_out[q].item(), :, 0] = self.tables[job_lut[q].item(), s[job_in[q].item(), :, 0]]
+            m = torch.remainder(s[job_in[q].item(), :, 0] >> 1, 2 * self.size)      # negacyclic over the padding bit
+            t = self.tables[job_lut[q].item(), torch.where(m >= self.size, m - self.size, m)]
+            o[job_out[q].item(), :, 0] = torch.where(m >= self.size, -t, t)
+
+
+def _messages(half_units, width):
+    """what decryption returns: the signed message mod 2^(width+1)"""
+    size = 1 << width
+    return np.mod(half_units // 2 + size, 2 * size) - size
 
 
 def _free_port():
@@ -55,13 +66,13 @@ def _worker(rank, world, port, path, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     z, prog = np.load(path), Program.load(path)
-    ex = Executor(prog, PR.TOY_1024, ClearEngine(), rank=rank, world=world, torch_device="cpu")
+    ex = Executor(prog, PR.TOY_1024, ClearEngine(prog.width), rank=rank, world=world, torch_device="cpu")
     x = z["golden_inputs"].astype(np.int64)[:3]
     batch = x.shape[0]
     ex._ensure(batch)
-    ex.vals[: prog.n_inputs, :, 0] = torch.from_numpy(x.T.copy())
+    ex.vals[: prog.n_inputs, :, 0] = torch.from_numpy(2 * x.T)
     ex.run_device(batch)
-    got = ex.outs[:, :, 0].numpy().T
+    got = _messages(ex.outs[:, :, 0].numpy().T, prog.width)
     ok = bool(np.array_equal(got, z["golden_outputs"].astype(np.int64)[:3])) and bool(np.array_equal(got, prog.evaluate_clear(x)))
     ret[rank] = ok
     dist.barrier()
@@ -92,9 +103,9 @@ def test_single_rank_clear_engine_matches_program():
     """the stand-in engine itself is faithful (world = 1 uses the unsharded path)"""
     path = os.path.join(HERE, "golden", "qf_mul_medium.npz")
     z, prog = np.load(path), Program.load(path)
-    ex = Executor(prog, PR.TOY_4096, ClearEngine(), torch_device="cpu")
+    ex = Executor(prog, PR.TOY_4096, ClearEngine(prog.width), torch_device="cpu")
     x = z["golden_inputs"].astype(np.int64)[:2]
     ex._ensure(2)
-    ex.vals[: prog.n_inputs, :, 0] = torch.from_numpy(x.T.copy())
+    ex.vals[: prog.n_inputs, :, 0] = torch.from_numpy(2 * x.T)
     ex.run_device(2)
-    assert np.array_equal(ex.outs[:, :, 0].numpy().T, z["golden_outputs"].astype(np.int64)[:2])
+    assert np.array_equal(_messages(ex.outs[:, :, 0].numpy().T, prog.width), z["golden_outputs"].astype(np.int64)[:2])
