@@ -357,6 +357,7 @@ def main():
                                       "peak_Tops": int_peak / 1e12, "frac": int_ops / (pbs_ms * 1e-3) / int_peak if pbs_ms else None,
                                       "note": "model count of 32-bit integer instructions the NTT external product needs (DESIGN.md section 5)"}},
             "parity_check": check,
+            "blind_rotation": {op: "pairs" if circuits[op].params.bsk_group == 2 else "single" for op in OPS},
         }
         if inv:
             line["inversion"] = inv

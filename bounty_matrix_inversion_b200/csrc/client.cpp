@@ -33,7 +33,7 @@ struct Rng {
     }
 };
 enum { ST_LWE_KEY = 1, ST_GLWE_KEY = 2, ST_BSK_MASK = 3, ST_BSK_NOISE = 4, ST_KSK_MASK = 5, ST_KSK_NOISE = 6,
-       ST_ENC_MASK = 7, ST_ENC_NOISE = 8 };
+       ST_ENC_MASK = 7, ST_ENC_NOISE = 8, ST_BSKP_MASK = 9, ST_BSKP_NOISE = 10 };
 
 // host negacyclic transform (merged-twiddle butterflies), used only to multiply masks by key polynomials
 struct HostNtt {
@@ -88,6 +88,37 @@ bool check(const bmi_params* p) {
     return true;
 }
 
+// `count` GGSW ciphertexts of the bits msg[i]: out[i][r][comp][t], r = c*l + (j-1), body last
+void gen_ggsw(const bmi_params* p, u64 seed, u64 st_mask, u64 st_noise, const u64* S, const u64* msg, int count, u64* out, int threads) {
+    const int k = p->k, N = p->N, l = p->bsk_l, rows = (k + 1) * l;
+    const HostNtt ntt(N);
+    std::vector<u64> Shat((size_t)k * N);
+    for (int m = 0; m < k; m++) {
+        std::memcpy(&Shat[(size_t)m * N], S + (size_t)m * N, sizeof(u64) * N);
+        ntt.fwd(&Shat[(size_t)m * N]);
+    }
+    const Rng rm(seed, st_mask), rn(seed, st_noise);
+    parallel_for((int64_t)count * rows, threads, [&](int64_t lo, int64_t hi) {
+        std::vector<u64> sum(N), tmp(N);
+        for (int64_t id = lo; id < hi; id++) {
+            u64* row = out + (size_t)id * (k + 1) * N;
+            u64* body = row + (size_t)k * N;
+            std::fill(sum.begin(), sum.end(), 0);
+            for (int m = 0; m < k; m++) {
+                u64* A = row + (size_t)m * N;
+                for (int t = 0; t < N; t++) A[t] = rm.field(((u64)id * k + m) * N + t);
+                std::memcpy(tmp.data(), A, sizeof(u64) * N);
+                ntt.fwd(tmp.data());
+                for (int t = 0; t < N; t++) sum[t] = fadd(sum[t], fmul(tmp[t], Shat[(size_t)m * N + t]));
+            }
+            ntt.inv(sum.data());
+            for (int t = 0; t < N; t++) body[t] = fadd(sum[t], rn.gauss((u64)id * N + t, p->glwe_sigma));
+            const int i = (int)(id / rows), r = (int)(id % rows), c = r / l, j = r % l + 1;
+            if (msg[i]) row[(size_t)c * N] = fadd(row[(size_t)c * N], 1ULL << (64 - j * p->bsk_bl));
+        }
+    });
+}
+
 }  // namespace
 
 extern "C" {
@@ -108,33 +139,19 @@ int bmi_keygen_glwe(const bmi_params* p, uint64_t seed, uint64_t* S) {
 
 int bmi_keygen_bsk(const bmi_params* p, uint64_t seed, const uint64_t* s, const uint64_t* S, uint64_t* bsk, int threads) {
     if (!check(p) || !s || !S || !bsk) return BMI_EINVAL;
-    const int k = p->k, N = p->N, l = p->bsk_l, rows = (k + 1) * l;
-    const HostNtt ntt(N);
-    std::vector<u64> Shat((size_t)k * N);
-    for (int m = 0; m < k; m++) {
-        std::memcpy(&Shat[(size_t)m * N], S + (size_t)m * N, sizeof(u64) * N);
-        ntt.fwd(&Shat[(size_t)m * N]);
+    gen_ggsw(p, seed, ST_BSK_MASK, ST_BSK_NOISE, S, s, p->n, bsk, threads);
+    return BMI_OK;
+}
+
+int bmi_keygen_bsk_pairs(const bmi_params* p, uint64_t seed, const uint64_t* s, const uint64_t* S, uint64_t* bskp, int threads) {
+    if (!check(p) || !s || !S || !bskp) return BMI_EINVAL;
+    if (p->n % 2) { bmi_host::set_error("pair key needs an even LWE dimension"); return BMI_EINVAL; }
+    std::vector<u64> msg((size_t)3 * (p->n / 2));
+    for (int q = 0; q < p->n / 2; q++) {
+        const u64 a = s[2 * q], b = s[2 * q + 1];
+        msg[3 * q] = a & b; msg[3 * q + 1] = a & (b ^ 1); msg[3 * q + 2] = (a ^ 1) & b;
     }
-    const Rng rm(seed, ST_BSK_MASK), rn(seed, ST_BSK_NOISE);
-    parallel_for((int64_t)p->n * rows, threads, [&](int64_t lo, int64_t hi) {
-        std::vector<u64> sum(N), tmp(N);
-        for (int64_t id = lo; id < hi; id++) {
-            u64* row = bsk + (size_t)id * (k + 1) * N;
-            u64* body = row + (size_t)k * N;
-            std::fill(sum.begin(), sum.end(), 0);
-            for (int m = 0; m < k; m++) {
-                u64* A = row + (size_t)m * N;
-                for (int t = 0; t < N; t++) A[t] = rm.field(((u64)id * k + m) * N + t);
-                std::memcpy(tmp.data(), A, sizeof(u64) * N);
-                ntt.fwd(tmp.data());
-                for (int t = 0; t < N; t++) sum[t] = fadd(sum[t], fmul(tmp[t], Shat[(size_t)m * N + t]));
-            }
-            ntt.inv(sum.data());
-            for (int t = 0; t < N; t++) body[t] = fadd(sum[t], rn.gauss((u64)id * N + t, p->glwe_sigma));
-            const int i = (int)(id / rows), r = (int)(id % rows), c = r / l, j = r % l + 1;
-            if (s[i]) row[(size_t)c * N] = fadd(row[(size_t)c * N], 1ULL << (64 - j * p->bsk_bl));
-        }
-    });
+    gen_ggsw(p, seed, ST_BSKP_MASK, ST_BSKP_NOISE, S, msg.data(), (int)msg.size(), bskp, threads);
     return BMI_OK;
 }
 

@@ -3,8 +3,10 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bmi_tfhe.h"
@@ -32,6 +34,12 @@ struct bmi_ctx {
     u64 ninv;
     u64 *d_tw = nullptr, *d_twi = nullptr, *d_ksk = nullptr, *d_luts = nullptr;
     u64* d_bsk[3] = {nullptr, nullptr, nullptr};   // transform-domain key: throughput build / latency build / 8-CTA split kernel
+    // pair blind rotation (bmi_ctx_load_bsk_pairs): the pair key in the same three layouts, per layout the exponent of
+    // every transform slot's evaluation point, and the powers of psi
+    u64* d_bskp[3] = {nullptr, nullptr, nullptr};
+    u32* d_expo[3] = {nullptr, nullptr, nullptr};
+    u64* d_pw = nullptr;
+    bool pairs = false;
     int n_luts = 0;
     int num_sms = 148;
     int64_t launches = 0;
@@ -65,6 +73,7 @@ template <int L>
 int setup_attrs(const bmi_ctx* c) {
     CK(cudaFuncSetAttribute(pbs_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
     CK(cudaFuncSetAttribute(pbs_split_async_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_split_async_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
     CK(cudaFuncSetAttribute(polymul_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SplitCfg<L>::M * 8));
     CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, split_convert_e<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
     if constexpr (L <= kMaxClusterL) {
@@ -74,6 +83,8 @@ int setup_attrs(const bmi_ctx* c) {
         CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
         if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
         CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
@@ -86,17 +97,17 @@ int setup_attrs(const bmi_ctx* c) {
 
 // both layouts of the transform-domain key: [0] throughput build (E = 4), [1] latency build
 template <int L>
-int launch_convert(bmi_ctx* c, const u64* src, int64_t p0, int64_t polys, cudaStream_t st) {
+int launch_convert(bmi_ctx* c, const u64* src, u64* const* dst, int64_t p0, int64_t polys, cudaStream_t st) {
     const size_t off = (size_t)p0 * c->p.N;
     if constexpr (L <= kMaxClusterL) {
         constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
-        bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, c->d_bsk[0] + off, c->d_tw, c->ninv);
-        bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, c->d_bsk[1] + off, c->d_tw, c->ninv);
+        bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, dst[0] + off, c->d_tw, c->ninv);
+        bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, dst[1] + off, c->d_tw, c->ninv);
         c->launches += 2;
     }
     if (c->p.bsk_l == 1) {
         constexpr int EC = split_convert_e<L>();
-        bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, c->d_bsk[2] + off, c->d_tw, c->ninv);
+        bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, dst[2] + off, c->d_tw, c->ninv);
         c->launches++;
     }
     CK(cudaGetLastError());
@@ -125,6 +136,13 @@ int64_t split_capacity(bmi_ctx* c) {
 
 template <int L>
 int launch_split(bmi_ctx* c, PbsArgs a, int64_t total, cudaStream_t st) {
+    if (c->pairs) {
+        a.bsk_hat = c->d_bskp[2]; a.expo = c->d_expo[2]; a.pw = c->d_pw;
+        pbs_split_async_kernel<L, true><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
+        c->launches++;
+        CK(cudaGetLastError());
+        return BMI_OK;
+    }
     a.bsk_hat = c->d_bsk[2];
     if (c->split_async) pbs_split_async_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
     else pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
@@ -153,6 +171,14 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
     a.bsk_hat = c->d_bsk[latency ? 1 : 0];
     const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
+    if (c->pairs) {
+        a.bsk_hat = c->d_bskp[latency ? 1 : 0]; a.expo = c->d_expo[latency ? 1 : 0]; a.pw = c->d_pw;
+        if (latency) pbs_cluster_kernel<L, EL, 1, true, false, true><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
+        else pbs_cluster_kernel<L, ET, TP, true, false, true><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
+        c->launches++;
+        CK(cudaGetLastError());
+        return BMI_OK;
+    }
     // GGSW rows staged by TMA whenever the extra 2N words still leave room for the CTAs per SM the build is sized for
     const bool stage = one && c->tma_stage && (latency ? (int)sms <= kMaxSmem : (int)sms * TP <= kMaxSmem);
     if (latency && stage) pbs_cluster_kernel<L, EL, 1, true, true><<<grid, NttCfg<L, EL>::T, sms, st>>>(a);
@@ -196,9 +222,31 @@ int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, 
     }
 
 int do_setup(bmi_ctx* c) { DISPATCH_L(c, setup_attrs<L>(c)); }
-int do_convert(bmi_ctx* c, const u64* s, int64_t p0, int64_t polys, cudaStream_t st) { DISPATCH_L(c, launch_convert<L>(c, s, p0, polys, st)); }
+int do_convert(bmi_ctx* c, const u64* s, u64* const* dst, int64_t p0, int64_t polys, cudaStream_t st) { DISPATCH_L(c, launch_convert<L>(c, s, dst, p0, polys, st)); }
 int do_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) { DISPATCH_L(c, launch_pbs<L>(c, a, st)); }
 int do_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* o, int n, cudaStream_t st) { DISPATCH_L(c, launch_polymul<L>(c, a, b, o, n, st)); }
+
+// upload a standard-domain key of `polys` polynomials in slices through a bounded staging buffer, converting slice by
+// slice into every transform-domain layout this parameter set can run (dst[0..2])
+int upload_converted(bmi_ctx* c, const u64* h_key, int64_t polys, u64** dst) {
+    const size_t bytes = (size_t)polys * c->p.N * 8;
+    for (int v = 0; v < 3; v++) {
+        const bool needed = v == 2 ? c->p.bsk_l == 1 : c->logN <= kMaxClusterL;
+        if (needed && !dst[v]) CK(cudaMalloc(&dst[v], bytes));
+    }
+    const int64_t slice = std::min<int64_t>(polys, 4096);
+    u64* stage = nullptr;
+    CK(cudaMalloc(&stage, (size_t)slice * c->p.N * 8));
+    for (int64_t p0 = 0; p0 < polys; p0 += slice) {
+        const int64_t cnt = std::min(slice, polys - p0);
+        CK(cudaMemcpy(stage, h_key + (size_t)p0 * c->p.N, (size_t)cnt * c->p.N * 8, cudaMemcpyHostToDevice));
+        int rc = do_convert(c, stage, dst, p0, cnt, 0);
+        if (rc) { cudaFree(stage); return rc; }
+        CK(cudaDeviceSynchronize());
+    }
+    cudaFree(stage);
+    return BMI_OK;
+}
 
 int ensure_scratch(bmi_ctx* c, int64_t count) {
     if (count <= c->w_cap) return BMI_OK;
@@ -265,6 +313,8 @@ int bmi_ctx_destroy(bmi_ctx* c) {
     cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk[0]); cudaFree(c->d_bsk[1]); cudaFree(c->d_bsk[2]); cudaFree(c->d_ksk); cudaFree(c->d_luts);
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
     cudaFree(c->ks_partial); cudaFree(c->d_ks_corr);
+    for (int v = 0; v < 3; v++) { cudaFree(c->d_bskp[v]); cudaFree(c->d_expo[v]); }
+    cudaFree(c->d_pw);
     delete c;
     return BMI_OK;
 }
@@ -272,25 +322,54 @@ int bmi_ctx_destroy(bmi_ctx* c) {
 int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
     if (!c || !h_bsk) { set_error("null argument"); return BMI_EINVAL; }
     CK(cudaSetDevice(c->device));
-    const int64_t polys = (int64_t)c->p.n * 2 * c->p.bsk_l * 2;
-    const size_t bytes = (size_t)polys * c->p.N * 8;
-    for (int v = 0; v < 3; v++) {
-        const bool needed = v == 2 ? c->p.bsk_l == 1 : c->logN <= kMaxClusterL;
-        if (needed && !c->d_bsk[v]) CK(cudaMalloc(&c->d_bsk[v], bytes));
+    return upload_converted(c, h_bsk, (int64_t)c->p.n * 2 * c->p.bsk_l * 2, c->d_bsk);
+}
+
+int bmi_ctx_load_bsk_pairs(bmi_ctx* c, const uint64_t* h_bskp) {
+    if (!c || !h_bskp) { set_error("null argument"); return BMI_EINVAL; }
+    if (c->p.bsk_l != 1 || c->p.n % 2) { set_error("pair blind rotation needs one decomposition level and an even LWE dimension"); return BMI_EINVAL; }
+    CK(cudaSetDevice(c->device));
+    int rc = upload_converted(c, h_bskp, (int64_t)(c->p.n / 2) * 3 * 2 * 2, c->d_bskp);
+    if (rc) return rc;
+    // powers of psi, and for every layout the exponent of each transform slot's evaluation point: the transform of
+    // the monomial X holds the evaluation points themselves (times 1/N, which the conversion folds in)
+    const int N = c->p.N;
+    const u64 psi = fpow(7, (BMI_P - 1) / (2 * (u64)N));
+    std::vector<u64> pw(2 * (size_t)N);
+    pw[0] = 1;
+    for (int t = 1; t < 2 * N; t++) pw[t] = fmul(pw[t - 1], psi);
+    if (!c->d_pw) CK(cudaMalloc(&c->d_pw, pw.size() * 8));
+    CK(cudaMemcpy(c->d_pw, pw.data(), pw.size() * 8, cudaMemcpyHostToDevice));
+    std::vector<std::pair<u64, u32>> index(pw.size());
+    for (u32 t = 0; t < pw.size(); t++) index[t] = {pw[t], t};
+    std::sort(index.begin(), index.end());
+    std::vector<u64> mono(N, 0);
+    mono[1] = 1;
+    u64 *d_src = nullptr, *d_dst[3] = {nullptr, nullptr, nullptr};
+    CK(cudaMalloc(&d_src, (size_t)N * 8));
+    CK(cudaMemcpy(d_src, mono.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+    for (int v = 0; v < 3; v++) CK(cudaMalloc(&d_dst[v], (size_t)N * 8));
+    rc = do_convert(c, d_src, d_dst, 0, 1, 0);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("transform of X failed"); rc = BMI_ECUDA; }
+    std::vector<u64> pts(N);
+    std::vector<u32> expo(N);
+    for (int v = 0; v < 3 && !rc; v++) {
+        if (!c->d_bskp[v]) continue;
+        if (cudaMemcpy(pts.data(), d_dst[v], (size_t)N * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy of transform of X failed"); rc = BMI_ECUDA; break; }
+        for (int u = 0; u < N; u++) {
+            const u64 point = fmul(pts[u], (u64)N);
+            auto it = std::lower_bound(index.begin(), index.end(), std::make_pair(point, (u32)0));
+            if (it == index.end() || it->first != point) { set_error("transform slot is not an evaluation at a power of psi"); rc = BMI_ESTATE; break; }
+            expo[u] = it->second;
+        }
+        if (rc) break;
+        if (!c->d_expo[v] && cudaMalloc(&c->d_expo[v], (size_t)N * 4) != cudaSuccess) { set_error("out of device memory"); rc = BMI_ENOMEM; break; }
+        if (cudaMemcpy(c->d_expo[v], expo.data(), (size_t)N * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("upload of exponents failed"); rc = BMI_ECUDA; }
     }
-    // upload in slices through a bounded staging buffer, converting slice by slice
-    const int64_t slice = std::min<int64_t>(polys, 4096);
-    u64* stage = nullptr;
-    CK(cudaMalloc(&stage, (size_t)slice * c->p.N * 8));
-    for (int64_t p0 = 0; p0 < polys; p0 += slice) {
-        const int64_t cnt = std::min(slice, polys - p0);
-        CK(cudaMemcpy(stage, h_bsk + (size_t)p0 * c->p.N, (size_t)cnt * c->p.N * 8, cudaMemcpyHostToDevice));
-        int rc = do_convert(c, stage, p0, cnt, 0);
-        if (rc) { cudaFree(stage); return rc; }
-        CK(cudaDeviceSynchronize());
-    }
-    cudaFree(stage);
-    return BMI_OK;
+    cudaFree(d_src);
+    for (int v = 0; v < 3; v++) cudaFree(d_dst[v]);
+    if (!rc) c->pairs = true;
+    return rc;
 }
 
 int bmi_ctx_load_ksk(bmi_ctx* c, const uint64_t* h_ksk) {
@@ -382,12 +461,13 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
 int bmi_pbs(bmi_ctx* c, const uint64_t* d_small, const int32_t* d_job_in, const int32_t* d_job_lut, const int32_t* d_job_out,
             uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
     if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
-    if (!(c->d_bsk[0] || c->d_bsk[2]) || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
+    if (!(c->d_bsk[0] || c->d_bsk[2] || c->pairs) || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
     if (njobs == 0) return BMI_OK;
     PbsArgs a;
     a.bsk_hat = nullptr; a.tw = c->d_tw; a.twi = c->d_twi; a.luts = c->d_luts; a.small = d_small;
     a.job_in = d_job_in; a.job_lut = d_job_lut; a.job_out = d_job_out; a.out = d_out;
     a.njobs = njobs; a.batch = batch; a.n = c->p.n; a.bl = c->p.bsk_bl; a.l = c->p.bsk_l;
+    a.expo = nullptr; a.pw = nullptr;
     return do_pbs(c, a, (cudaStream_t)stream);
 }
 

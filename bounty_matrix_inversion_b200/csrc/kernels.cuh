@@ -14,7 +14,30 @@ struct PbsArgs {
     u64* __restrict__ out;             // [rows][N+1] big-key LWE
     int njobs, batch;
     int n, bl, l;
+    // pair blind rotation (two key bits per step): bsk_hat is then the pair key [n/2][3][2][2][N]
+    const u32* __restrict__ expo;      // [N] transform slot (in bsk_hat's layout) -> r with evaluation point psi^r
+    const u64* __restrict__ pw;        // [2N] psi^t
 };
+
+// Pair blind rotation, transform domain: the GGSW the step multiplies the decomposed accumulator with is
+//   (X^(a1+a2) - 1) K11 + (X^a1 - 1) K10 + (X^a2 - 1) K01
+// and a monomial X^e is, at the slot whose evaluation point is psi^r, the scalar psi^(e r mod 2N).
+struct PairMono {
+    u64 m11, m10, m01;      // lazy
+};
+__device__ __forceinline__ PairMono pair_monomials(const PbsArgs& a, u32 slot, u32 a1, u32 a2, u32 mask2n) {
+    const u32 e = __ldg(a.expo + slot);
+    const u64 p10 = __ldg(a.pw + ((a1 * e) & mask2n)), p01 = __ldg(a.pw + ((a2 * e) & mask2n));
+    PairMono m;
+    m.m11 = fsub_l(fmul_l(p10, p01), 1);
+    m.m10 = fsub_l(p10, 1);
+    m.m01 = fsub_l(p01, 1);
+    return m;
+}
+// m11 k11 + m10 k10 + m01 k01, lazy
+__device__ __forceinline__ u64 pair_combine(const PairMono& m, u64 k11, u64 k10, u64 k01) {
+    return fadd_l(fadd_l(fmul_c(m.m11, k11), fmul_l(m.m10, k10)), fmul_c(m.m01, k01));
+}
 
 // The two builds of the bootstrap kernel per polynomial size: coefficients per thread (log2) and the CTAs per SM
 // the register budget is sized for.  Latency build: as many warps per transform as a CTA allows, all in registers.
@@ -144,8 +167,11 @@ __device__ __forceinline__ void mbar_wait_cluster(u64* bar, u32 parity) {
 
 //   STAGE     (ONE_LEVEL only) the two GGSW row polynomials of the next CMUX are brought into shared memory by one
 //             TMA bulk copy issued a whole CMUX ahead, instead of per-thread global loads after the transform
-template <int L, int E, int MINB, bool ONE_LEVEL, bool STAGE>
+//   PAIR      (ONE_LEVEL, no STAGE) two key bits per step with the pair key: the accumulator itself is decomposed (no
+//             rotated reads), one forward/inverse transform serves both bits, the monomials enter the pointwise stage
+template <int L, int E, int MINB, bool ONE_LEVEL, bool STAGE, bool PAIR = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
+    static_assert(!PAIR || (ONE_LEVEL && !STAGE), "pair blind rotation: one decomposition level, no TMA staging");
     using C = NttCfg<L, E>;
     constexpr int N = C::N, T = C::T, EPT = C::EPT;
     extern __shared__ u64 smem[];
@@ -203,13 +229,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
         __syncthreads();
         if (STAGE && tid == 0) prefetch_rows(0);
 
-        for (int i = 0; i < n; i++) {
-            const u32 at = rot[i];
-            if (at == 0) continue;    // X^0 - 1 = 0: nothing to add (same decision in both CTAs)
+        for (int i = 0; i < n; i += PAIR ? 2 : 1) {
+            const u32 at = rot[i], at2 = PAIR ? rot[i + 1] : 0;
+            if ((at | at2) == 0) continue;    // X^0 - 1 = 0: nothing to add (same decision in both CTAs)
             if (tid == 0) mbar_expect(&xbar[0], N * 8);
             u64 own[EPT];
             const u64* g = a.bsk_hat + ((size_t)i * (2 * l) + me * l) * 2 * N;
-            if (ONE_LEVEL) {
+            if (PAIR) {
+                u64 x[EPT];
+#pragma unroll
+                for (int q = 0; q < EPT; q++) x[q] = digit_of(round_top(acc[q * T + tid], tot), bl, 1, 1);
+                ntt_forward<L, E>(x, buf, a.tw, tid);
+                mbar_wait_cluster(&xbar[1], ph_x);     // partner has consumed what I pushed for the previous step
+                // pair key: [pair][K11, K10, K01][row = decomposed polynomial][output polynomial][N]
+                const u64* gp = a.bsk_hat + ((size_t)(i >> 1) * 6 + me) * 2 * N;
+#pragma unroll
+                for (int q = 0; q < EPT; q++) {
+                    const int idx = q * T + tid;
+                    const PairMono m = pair_monomials(a, idx, at, at2, 2 * N - 1);
+                    const u64 ko = pair_combine(m, __ldg(gp + other * N + idx), __ldg(gp + 4 * N + other * N + idx),
+                                                __ldg(gp + 8 * N + other * N + idx));
+                    st_async_u64(peer_recv_a + (u32)idx * 8, fmul_c(x[q], ko), peer_rcv_bar);
+                    const u64 km = pair_combine(m, __ldg(gp + me * N + idx), __ldg(gp + 4 * N + me * N + idx),
+                                                __ldg(gp + 8 * N + me * N + idx));
+                    own[q] = fmul_l(x[q], km);
+                }
+            } else if (ONE_LEVEL) {
                 u64 x[EPT];
 #pragma unroll
                 for (int q = 0; q < EPT; q++) {   // the digit of (X^at - 1) * acc

@@ -223,7 +223,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
 // that its reader sends AFTER the read (gbuf, lbuf, acc), or the buffer is double-buffered (recv).
 // (Folding the partial-sum exchange into the inverse all-to-all via linearity of the inverse transform was tried:
 //  same time, more DSMEM traffic -- not kept.)
-template <int L>
+// PAIR: two key bits per step with the pair key (kernels.cuh).  The accumulator itself is decomposed, so no CTA reads
+// another CTA's accumulator and the acc_bar round disappears along with half of the steps.
+template <int L, bool PAIR = false>
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) pbs_split_async_kernel(const PbsArgs a) {
     using C = SplitCfg<L>;
     using LC = typename C::Local;
@@ -278,20 +280,23 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
             }
         }
         __syncthreads();
-        if (tid < 4) mbar_arrive_remote(acc_bar_r[tid]);      // my accumulator is ready
+        if (!PAIR && tid < 4) mbar_arrive_remote(acc_bar_r[tid]);      // my accumulator is ready
 
-        for (int i = 0; i < n; i++) {
-            const u32 at = rot[i];
-            if (at == 0) continue;
+        for (int i = 0; i < n; i += PAIR ? 2 : 1) {
+            const u32 at = rot[i], at2 = PAIR ? rot[i + 1] : 0;
+            if ((at | at2) == 0) continue;
             if (tid == 0) {           // post what this CMUX will receive
                 mbar_expect(&bars[1], M * 8);
                 mbar_expect(&bars[2], M * 8);
                 mbar_expect(&bars[3], M * 8);
             }
-            mbar_wait_cluster(&bars[0], ph_acc);
-            ph_acc ^= 1;
             u64 x[4];
-            {
+            if (PAIR) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) x[q] = digit_of(round_top(acc[q * T + tid], bl), bl, 1, 1);
+            } else {
+                mbar_wait_cluster(&bars[0], ph_acc);
+                ph_acc ^= 1;
                 const u64* src = cluster_map(acc, group0 + ((r - at) & 3));
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -325,13 +330,28 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
                 butterfly<false>(x[2], x[3], __ldg(a.tw + (1 << (L - 1)) + 2 * blk + 1));
             }
             // ---- pointwise products; the partner polynomial's share goes to the partner CTA
-            const u64* g = a.bsk_hat + ((size_t)i * 2 + c) * 2 * N + (size_t)r * M;
             u64 own[4];
             const u32 rbase = recv_r + (ph ? (u32)M * 8 : 0);
+            if (PAIR) {
+                // pair key: [pair][K11, K10, K01][row = decomposed polynomial][output polynomial][N], split layout within N
+                const u64* gp = a.bsk_hat + ((size_t)(i >> 1) * 6 + c) * 2 * N + (size_t)r * M;
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                st_async_u64(rbase + (u32)(e * T + tid) * 8, fmul_c(x[e], __ldg(g + (size_t)(c ^ 1) * N + e * T + tid)), rcv_bar_r);
-                own[e] = fmul_l(x[e], __ldg(g + (size_t)c * N + e * T + tid));
+                for (int e = 0; e < 4; e++) {
+                    const int idx = e * T + tid;
+                    const PairMono m = pair_monomials(a, (u32)r * M + idx, at, at2, 2 * N - 1);
+                    const size_t oc = (size_t)(c ^ 1) * N + idx, mc = (size_t)c * N + idx;
+                    const u64 ko = pair_combine(m, __ldg(gp + oc), __ldg(gp + 4 * N + oc), __ldg(gp + 8 * N + oc));
+                    st_async_u64(rbase + (u32)idx * 8, fmul_c(x[e], ko), rcv_bar_r);
+                    const u64 km = pair_combine(m, __ldg(gp + mc), __ldg(gp + 4 * N + mc), __ldg(gp + 8 * N + mc));
+                    own[e] = fmul_l(x[e], km);
+                }
+            } else {
+                const u64* g = a.bsk_hat + ((size_t)i * 2 + c) * 2 * N + (size_t)r * M;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    st_async_u64(rbase + (u32)(e * T + tid) * 8, fmul_c(x[e], __ldg(g + (size_t)(c ^ 1) * N + e * T + tid)), rcv_bar_r);
+                    own[e] = fmul_l(x[e], __ldg(g + (size_t)c * N + e * T + tid));
+                }
             }
             mbar_wait(&bars[2], ph);
             {
@@ -360,11 +380,13 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
                 acc[lc] = fcanon(fadd_l(own[q], acc[lc]));
             }
             __syncthreads();
-            if (tid < 4) mbar_arrive_remote(acc_bar_r[tid]);
+            if (!PAIR && tid < 4) mbar_arrive_remote(acc_bar_r[tid]);
         }
 
-        mbar_wait_cluster(&bars[0], ph_acc);      // consume the last "accumulator ready" round
-        ph_acc ^= 1;
+        if (!PAIR) {
+            mbar_wait_cluster(&bars[0], ph_acc);      // consume the last "accumulator ready" round
+            ph_acc ^= 1;
+        }
         if (c == 0) {
 #pragma unroll
             for (int q = 0; q < 4; q++) {

@@ -3,6 +3,7 @@ reference drives (/root/reference/matrix_inversion/main.py:53-116,
 qfloat_matrix_inversion.py:978-1052), implemented on the B200 engine."""
 from __future__ import annotations
 
+import dataclasses
 import inspect
 import time
 
@@ -17,7 +18,9 @@ class Configuration:
     """accepts Concrete's keyword options; the ones this engine understands:
     tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, seed, device,
     multiplication ("auto" | "quarter_square", see tracing.Trace),
-    split_wide ("auto" | True | False) and split_guard (see program.lower)"""
+    split_wide ("auto" | True | False) and split_guard (see program.lower),
+    blind_rotation ("pairs" | "single"): two key bits per bootstrap step with the pair key (default wherever the
+    parameter set has one decomposition level and an even LWE dimension), or one GGSW per key bit"""
 
     def __init__(self, **options):
         self.options = dict(options)
@@ -29,6 +32,9 @@ class Configuration:
         self.multiplication = options.get("multiplication", "auto")
         self.split_wide = options.get("split_wide", "auto")
         self.split_guard = options.get("split_guard")
+        self.blind_rotation = options.get("blind_rotation", "pairs")
+        if self.blind_rotation not in ("pairs", "single"):
+            raise ValueError("blind_rotation must be 'pairs' or 'single'")
 
     def fork(self, **options):
         merged = dict(self.options)
@@ -98,15 +104,23 @@ class Compiler:
         prog = lower(trace, flat_out, (n_out,), slack_bits=cfg.slack_bits, split_wide=cfg.split_wide,
                      split_guard=cfg.split_guard)
         t2 = time.time()
-        prm = None if cfg.tfhe_params == "deferred" else (cfg.tfhe_params or PR.for_width(prog.width, prog.nu2))
+        prm = None if cfg.tfhe_params == "deferred" else (cfg.tfhe_params or _select_params(prog, cfg))
         prog.stats.update(trace_s=round(t1 - t0, 3), lower_s=round(t2 - t1, 3), params_s=round(time.time() - t2, 3))
         if verbose:
             print("compiled:", prog.stats, prm)
         return Circuit(prog, prm, in_shapes, out_shapes, cfg)
 
 
+def _select_params(program: Program, cfg: Configuration) -> PR.TfheParams:
+    return PR.for_width(program.width, program.nu2, bsk_group=2 if cfg.blind_rotation == "pairs" else 1)
+
+
 class Circuit:
     def __init__(self, program: Program, params: PR.TfheParams, in_shapes, out_shapes, cfg: Configuration):
+        if params is not None:
+            # explicit parameter sets follow the configuration too, where the pair blind rotation can run them
+            pairs = cfg.blind_rotation == "pairs" and params.bsk_l == 1 and params.n % 2 == 0
+            params = dataclasses.replace(params, bsk_group=2 if pairs else 1)
         self.program, self.params, self.cfg = program, params, cfg
         self.in_shapes, self.out_shapes = [tuple(s) for s in in_shapes], [tuple(s) for s in out_shapes]
         self.keys = None
@@ -117,7 +131,7 @@ class Circuit:
     def from_program(cls, program: Program, params=None, in_shapes=None, out_shapes=None, configuration=None):
         """a compiled Program (e.g. Program.load of a .npz traced elsewhere) -> runnable circuit"""
         cfg = configuration or Configuration()
-        prm = params or cfg.tfhe_params or PR.for_width(program.width, program.nu2)
+        prm = params or cfg.tfhe_params or _select_params(program, cfg)
         in_shapes = in_shapes or [(program.n_inputs,)]
         out_shapes = out_shapes or [tuple(program.out_shape)]
         return cls(program, prm, in_shapes, out_shapes, cfg)
@@ -131,7 +145,7 @@ class Circuit:
     def keygen(self, force=False, seed=None):
         from ..native import ClientKeys
         if self.keys is None or force:
-            self.keys = ClientKeys(self.params, self.cfg.seed if seed is None else seed)
+            self.keys = ClientKeys(self.params, self.cfg.seed if seed is None else seed, pairs=self.params.bsk_group == 2)
             self._executor = None
         return self.keys
 
@@ -188,7 +202,7 @@ class Circuit:
             self.keygen()
             dev = self.cfg.device if device is None else device
             eng = Engine(self.params, dev)
-            eng.load_keys(self.keys.bsk, self.keys.ksk)
+            eng.load_keys(self.keys.bsk, self.keys.ksk, bskp=self.keys.bskp)
             self._executor = Executor(self.program, self.params, eng, dev, rank, world, group)
         return self._executor
 

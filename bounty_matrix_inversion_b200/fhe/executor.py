@@ -81,7 +81,12 @@ class Executor:
         jobs = sum(j for _, _, j in prof)
         per_pbs_bytes = p.bsk_bytes() + (p.n + 1) * 8 + p.N * 8 + (p.big_dim + 1) * 8
         butterflies = (p.k + 1) * (p.bsk_l + 1) * (p.N // 2) * p.logN
-        per_pbs_int = p.n * (butterflies * 26 + (p.k + 1) ** 2 * p.bsk_l * p.N * 22 + (p.k + 1) * p.bsk_l * p.N * 12)
+        per_step = butterflies * 26 + (p.k + 1) ** 2 * p.bsk_l * p.N * 22 + (p.k + 1) * p.bsk_l * p.N * 12
+        if p.bsk_group == 2:
+            # pair key: per slot and CTA one product + three subtractions for the monomials, six products + four
+            # additions to combine the three keys for both output polynomials, two products with the digits
+            per_step = butterflies * 26 + (p.k + 1) * p.N * (9 * 22 + 7 * 3) + (p.k + 1) * p.bsk_l * p.N * 12
+        per_pbs_int = (p.n // p.bsk_group) * per_step
         out = {"pbs_ms": ms, "pbs_launches": len(prof), "pbs_jobs": jobs, "alg_bytes": jobs * per_pbs_bytes,
                "int_ops": jobs * per_pbs_int}
         if origin is not None:

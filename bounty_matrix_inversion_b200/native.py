@@ -37,12 +37,14 @@ _SIGNATURES = {
     "bmi_keygen_lwe": (C.c_int, [C.c_void_p, C.c_uint64, U64P]),
     "bmi_keygen_glwe": (C.c_int, [C.c_void_p, C.c_uint64, U64P]),
     "bmi_keygen_bsk": (C.c_int, [C.c_void_p, C.c_uint64, U64P, U64P, U64P, C.c_int]),
+    "bmi_keygen_bsk_pairs": (C.c_int, [C.c_void_p, C.c_uint64, U64P, U64P, U64P, C.c_int]),
     "bmi_keygen_ksk": (C.c_int, [C.c_void_p, C.c_uint64, U64P, U64P, U64P, C.c_int]),
     "bmi_lwe_encrypt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, U64P, U64P, C.c_int64, U64P]),
     "bmi_lwe_phase": (C.c_int, [U64P, C.c_int32, U64P, C.c_int64, U64P]),
     "bmi_ctx_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bmi_ctx_destroy": (C.c_int, [C.c_void_p]),
     "bmi_ctx_load_bsk": (C.c_int, [C.c_void_p, U64P]),
+    "bmi_ctx_load_bsk_pairs": (C.c_int, [C.c_void_p, U64P]),
     "bmi_ctx_load_ksk": (C.c_int, [C.c_void_p, U64P]),
     "bmi_ctx_load_luts": (C.c_int, [C.c_void_p, U64P, C.c_int32]),
     "bmi_ctx_launch_count": (C.c_int64, [C.c_void_p]),
@@ -92,7 +94,10 @@ def _u64(a):
 class ClientKeys:
     """secret and evaluation keys of one circuit (host memory)"""
 
-    def __init__(self, params: TfheParams, seed: int, threads: int = 0, evaluation_keys: bool = True):
+    def __init__(self, params: TfheParams, seed: int, threads: int = 0, evaluation_keys: bool = True,
+                 pairs: bool = False):
+        """pairs: generate the pair bootstrapping key (two key bits per blind-rotation step, `bskp`) instead of the
+        one-GGSW-per-bit key (`bsk`)"""
         self.params, self.seed = params, int(seed)
         bp = BmiParams.of(params)
         L = lib()
@@ -101,11 +106,16 @@ class ClientKeys:
         self.S = np.zeros(params.big_dim, np.uint64)
         _check(L.bmi_keygen_lwe(C.byref(bp), self.seed, _p(self.s)))
         _check(L.bmi_keygen_glwe(C.byref(bp), self.seed, _p(self.S)))
-        self.bsk = self.ksk = None
+        self.bsk = self.bskp = self.ksk = None
         if evaluation_keys:
-            self.bsk = np.zeros((params.n, (params.k + 1) * params.bsk_l, params.k + 1, params.N), np.uint64)
+            rows = (params.k + 1) * params.bsk_l
             self.ksk = np.zeros((params.big_dim, params.ksk_l, params.n + 1), np.uint64)
-            _check(L.bmi_keygen_bsk(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.bsk), threads))
+            if pairs:
+                self.bskp = np.zeros((params.n // 2, 3, rows, params.k + 1, params.N), np.uint64)
+                _check(L.bmi_keygen_bsk_pairs(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.bskp), threads))
+            else:
+                self.bsk = np.zeros((params.n, rows, params.k + 1, params.N), np.uint64)
+                _check(L.bmi_keygen_bsk(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.bsk), threads))
             _check(L.bmi_keygen_ksk(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.ksk), threads))
 
     def encrypt(self, plaintexts, ct_index0: int = 0) -> np.ndarray:
@@ -146,10 +156,13 @@ class Engine:
         except Exception:
             pass
 
-    def load_keys(self, bsk: np.ndarray, ksk: np.ndarray):
-        bsk, ksk = _u64(bsk), _u64(ksk)
-        _check(lib().bmi_ctx_load_bsk(self._h, _p(bsk)))
-        _check(lib().bmi_ctx_load_ksk(self._h, _p(ksk)))
+    def load_keys(self, bsk, ksk: np.ndarray, bskp=None):
+        """bsk: one GGSW per key bit; bskp: pair key (then bootstraps rotate two key bits per step); either may be None"""
+        if bsk is not None:
+            _check(lib().bmi_ctx_load_bsk(self._h, _p(_u64(bsk))))
+        if bskp is not None:
+            _check(lib().bmi_ctx_load_bsk_pairs(self._h, _p(_u64(bskp))))
+        _check(lib().bmi_ctx_load_ksk(self._h, _p(_u64(ksk))))
 
     def load_luts(self, luts: np.ndarray):
         luts = _u64(luts).reshape(-1, self.params.N)

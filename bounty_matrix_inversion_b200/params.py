@@ -36,6 +36,7 @@ class TfheParams:
     ksk_l: int          # keyswitch levels
     lwe_sigma: float    # small-key noise std, units of 2^-64
     glwe_sigma: float   # GLWE / big-key noise std, units of 2^-64
+    bsk_group: int = 1  # key bits per blind-rotation step: 1 = one GGSW per bit, 2 = pair key (3 GGSWs per 2 bits)
 
     @property
     def big_dim(self):
@@ -46,7 +47,8 @@ class TfheParams:
         return self.N.bit_length() - 1
 
     def bsk_bytes(self):
-        return self.n * (self.k + 1) * self.bsk_l * (self.k + 1) * self.N * 8
+        ggsws = self.n if self.bsk_group == 1 else 3 * (self.n // 2)
+        return ggsws * (self.k + 1) * self.bsk_l * (self.k + 1) * self.N * 8
 
     def ksk_bytes(self):
         return self.big_dim * self.ksk_l * (self.n + 1) * 8
@@ -103,10 +105,12 @@ def secure_std(dim: int) -> float:
 
 
 def variance_blind_rotate(p: TfheParams) -> float:
+    """one GGSW external product per key bit; with the pair key each step of two bits adds three products, each
+    multiplied by a monomial minus one (two coefficients: twice the variance): 3x the noise per bit"""
     B2 = 4.0 ** p.bsk_bl
     vb = (p.glwe_sigma / TWO64) ** 2
     per = p.bsk_l * (p.k + 1) * p.N * (B2 + 2) / 12.0 * vb + (1 + p.k * p.N / 2.0) / (24.0 * B2 ** p.bsk_l)
-    return p.n * per
+    return p.n * per * (3.0 if p.bsk_group == 2 else 1.0)
 
 
 def variance_keyswitch(p: TfheParams) -> float:
@@ -134,20 +138,22 @@ def cost(p: TfheParams) -> float:
     """integer multiply count of keyswitch + PBS (what both the CPU and the GPU path pay)"""
     ntt = (p.k + 1) * (p.bsk_l + 1) * (p.N / 2) * p.logN
     pointwise = (p.k + 1) ** 2 * p.bsk_l * p.N
-    return p.n * (ntt + pointwise) + p.big_dim * p.ksk_l * (p.n + 1)
+    steps = p.n if p.bsk_group == 1 else p.n / 2 * (1 + 4 * pointwise / (ntt + pointwise))     # 3 keys combined per slot
+    return steps * (ntt + pointwise) + p.big_dim * p.ksk_l * (p.n + 1)
 
 
-def optimize(width: int, nu2: float = 1.0, z: float = 6.5, k: int = 1, max_logN: int = 14) -> TfheParams:
+def optimize(width: int, nu2: float = 1.0, z: float = 6.5, k: int = 1, max_logN: int = 14, bsk_group: int = 1) -> TfheParams:
     """cheapest 128-bit-secure set whose lookups of `width`-bit messages fail with
-    probability < erfc(z / sqrt 2)"""
+    probability < erfc(z / sqrt 2); bsk_group = 2 selects among sets the pair blind rotation runs (one
+    decomposition level, even n) with its noise"""
     best = None
     for logN in range(max(width + 1, 9), max_logN + 1):
         N = 1 << logN
         gs = secure_std(k * N)
         for n in range(480, 1201, 8):
             ls = secure_std(n)
-            for bl_l in ((bl, l) for l in range(1, 5) for bl in range(4, 33) if bl * l <= 48):
-                base = TfheParams("", n, k, N, bl_l[0], bl_l[1], 1, 1, ls * TWO64, gs * TWO64)
+            for bl_l in ((bl, l) for l in range(1, 5 if bsk_group == 1 else 2) for bl in range(4, 33) if bl * l <= 48):
+                base = TfheParams("", n, k, N, bl_l[0], bl_l[1], 1, 1, ls * TWO64, gs * TWO64, bsk_group)
                 vbr = nu2 * variance_blind_rotate(base) + variance_modswitch(base)
                 budget = (0.5 ** (width + 2) / z) ** 2 - vbr
                 if budget <= 0:
@@ -167,7 +173,7 @@ def optimize(width: int, nu2: float = 1.0, z: float = 6.5, k: int = 1, max_logN:
     if best is None:
         raise ValueError(f"no parameter set for width={width} nu2={nu2}")
     p = best[1]
-    return replace(p, name=f"opt_w{width}_nu{int(nu2)}_n{p.n}_N{p.N}")
+    return replace(p, name=f"opt_w{width}_nu{int(nu2)}_n{p.n}_N{p.N}" + ("_pairs" if bsk_group == 2 else ""))
 
 
 # ----------------------------------------------------------------- presets
@@ -193,8 +199,13 @@ def _secure(name, n, N, bbl, bl, kbl, kl):
 SECURE = {}
 
 
-def for_width(width: int, nu2: float = 1.0) -> TfheParams:
-    key = (width, int(math.ceil(nu2)))
+def for_width(width: int, nu2: float = 1.0, bsk_group: int = 1) -> TfheParams:
+    key = (width, int(math.ceil(nu2)), bsk_group)
     if key not in SECURE:
-        SECURE[key] = optimize(width, nu2)
+        try:
+            SECURE[key] = optimize(width, nu2, bsk_group=bsk_group)
+        except ValueError:
+            if bsk_group == 1:
+                raise
+            SECURE[key] = optimize(width, nu2)          # no one-level set for this width: one GGSW per bit
     return SECURE[key]

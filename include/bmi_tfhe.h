@@ -53,6 +53,9 @@ int bmi_keygen_lwe(const bmi_params* p, uint64_t seed, uint64_t* h_s /* [n] */);
 int bmi_keygen_glwe(const bmi_params* p, uint64_t seed, uint64_t* h_S /* [k*N] */);
 /* bsk[i][r][comp][t]: i<n, r = c*l+(j-1) < (k+1)*l, comp<=k (k = body), coefficient domain */
 int bmi_keygen_bsk(const bmi_params* p, uint64_t seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_bsk, int threads);
+/* pair key for blind rotation two key bits per step (n even): bskp[q][x][r][comp][t], q<n/2,
+ * x = 0: GGSW(s_2q s_2q+1), 1: GGSW(s_2q (1 - s_2q+1)), 2: GGSW((1 - s_2q) s_2q+1); 1.5x the size of bsk */
+int bmi_keygen_bsk_pairs(const bmi_params* p, uint64_t seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_bskp, int threads);
 /* ksk[i][j-1][0..n]: i<k*N, body last */
 int bmi_keygen_ksk(const bmi_params* p, uint64_t seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_ksk, int threads);
 /* `count` big-key encryptions of the plaintexts h_pt (field elements); ciphertext q uses counter ct_index0+q */
@@ -65,6 +68,9 @@ int bmi_lwe_phase(const uint64_t* h_key, int32_t dim, const uint64_t* h_ct, int6
 int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out);
 int bmi_ctx_destroy(bmi_ctx* ctx);
 int bmi_ctx_load_bsk(bmi_ctx* ctx, const uint64_t* h_bsk);   /* upload + convert to the transform-domain layout */
+/* upload + convert the pair key; from then on bmi_pbs / bmi_ks_pbs_host rotate two key bits per step (bsk_l == 1 only):
+ * half the sequential transforms per bootstrap, same message, slightly different noise */
+int bmi_ctx_load_bsk_pairs(bmi_ctx* ctx, const uint64_t* h_bskp);
 int bmi_ctx_load_ksk(bmi_ctx* ctx, const uint64_t* h_ksk);
 int bmi_ctx_load_luts(bmi_ctx* ctx, const uint64_t* h_luts, int32_t n_luts);   /* [n_luts][N] accumulator polynomials */
 int64_t bmi_ctx_launch_count(const bmi_ctx* ctx);            /* kernels launched by this context so far */

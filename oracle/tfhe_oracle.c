@@ -84,7 +84,8 @@ static u64 rng_gauss(u64 seed, u64 stream, u64 ctr, double sigma) {
     return from_i64((i64)llround(z * sigma));
 }
 enum { ST_LWE_KEY = 1, ST_GLWE_KEY = 2, ST_BSK_MASK = 3, ST_BSK_NOISE = 4,
-       ST_KSK_MASK = 5, ST_KSK_NOISE = 6, ST_ENC_MASK = 7, ST_ENC_NOISE = 8 };
+       ST_KSK_MASK = 5, ST_KSK_NOISE = 6, ST_ENC_MASK = 7, ST_ENC_NOISE = 8,
+       ST_BSKP_MASK = 9, ST_BSKP_NOISE = 10 };
 
 u64 orc_rng_raw(u64 seed, u64 stream, u64 ctr) { return rng_raw(seed, stream, ctr); }
 u64 orc_rng_gauss(u64 seed, u64 stream, u64 ctr, double sigma) { return rng_gauss(seed, stream, ctr, sigma); }
@@ -157,26 +158,42 @@ typedef struct {
 void orc_keygen_lwe(u64 seed, int n, u64 *s) { for (int i = 0; i < n; i++) s[i] = rng_bit(seed, ST_LWE_KEY, i); }
 void orc_keygen_glwe(u64 seed, int k, int N, u64 *S) { for (int i = 0; i < k * N; i++) S[i] = rng_bit(seed, ST_GLWE_KEY, i); }
 
-/* bsk[i][r][comp][t], r = c*l + (j-1), comp in [0,k] (k = body); standard (coefficient) domain */
-void orc_keygen_bsk(u64 seed, const params_t *pp, const u64 *s, const u64 *S, u64 *bsk) {
-    int n = pp->n, k = pp->k, N = pp->N, l = pp->bsk_l, rows = (k + 1) * l;
+/* `count` GGSW ciphertexts of the bits msg[i]: out[i][r][comp][t], r = c*l + (j-1), comp in [0,k] (k = body);
+ * standard (coefficient) domain */
+static void gen_ggsw(u64 seed, u64 st_mask, u64 st_noise, const params_t *pp, const u64 *S, const u64 *msg, int count, u64 *out) {
+    int k = pp->k, N = pp->N, l = pp->bsk_l, rows = (k + 1) * l;
     u64 *tmp = malloc(sizeof(u64) * N);
-    for (int i = 0; i < n; i++) for (int r = 0; r < rows; r++) {
+    for (int i = 0; i < count; i++) for (int r = 0; r < rows; r++) {
         u64 row_id = (u64)i * rows + r;
-        u64 *row = bsk + row_id * (k + 1) * N;
+        u64 *row = out + row_id * (k + 1) * N;
         u64 *body = row + (u64)k * N;
-        for (int t = 0; t < N; t++) body[t] = rng_gauss(seed, ST_BSK_NOISE, row_id * N + t, pp->glwe_sigma);
+        for (int t = 0; t < N; t++) body[t] = rng_gauss(seed, st_noise, row_id * N + t, pp->glwe_sigma);
         for (int m = 0; m < k; m++) {
             u64 *A = row + (u64)m * N;
-            for (int t = 0; t < N; t++) A[t] = rng_field(seed, ST_BSK_MASK, (row_id * k + m) * N + t);
+            for (int t = 0; t < N; t++) A[t] = rng_field(seed, st_mask, (row_id * k + m) * N + t);
             negacyclic_mul(A, S + (u64)m * N, tmp, N);
             for (int t = 0; t < N; t++) body[t] = fadd(body[t], tmp[t]);
         }
         int c = r / l, j = r % l + 1;
         u64 g = 1ULL << (64 - j * pp->bsk_bl);
-        if (s[i]) row[(u64)c * N] = fadd(row[(u64)c * N], g);
+        if (msg[i]) row[(u64)c * N] = fadd(row[(u64)c * N], g);
     }
     free(tmp);
+}
+/* bsk[i] = GGSW(s_i) */
+void orc_keygen_bsk(u64 seed, const params_t *pp, const u64 *s, const u64 *S, u64 *bsk) {
+    gen_ggsw(seed, ST_BSK_MASK, ST_BSK_NOISE, pp, S, s, pp->n, bsk);
+}
+/* pair key (n even): bskp[q][0] = GGSW(s_2q s_2q+1), [q][1] = GGSW(s_2q (1 - s_2q+1)), [q][2] = GGSW((1 - s_2q) s_2q+1) */
+void orc_keygen_bsk_pairs(u64 seed, const params_t *pp, const u64 *s, const u64 *S, u64 *bskp) {
+    int np = pp->n / 2;
+    u64 *msg = malloc(sizeof(u64) * 3 * np);
+    for (int q = 0; q < np; q++) {
+        u64 a = s[2 * q], b = s[2 * q + 1];
+        msg[3 * q] = a & b; msg[3 * q + 1] = a & (b ^ 1); msg[3 * q + 2] = (a ^ 1) & b;
+    }
+    gen_ggsw(seed, ST_BSKP_MASK, ST_BSKP_NOISE, pp, S, msg, 3 * np, bskp);
+    free(msg);
 }
 /* ksk[i][j-1][0..n], body last */
 void orc_keygen_ksk(u64 seed, const params_t *pp, const u64 *s, const u64 *S, u64 *ksk) {
@@ -267,6 +284,43 @@ void orc_pbs(const params_t *pp, const u64 *bsk, const u64 *lut, const u64 *in, 
     }
     out[(u64)k * N] = acc[(u64)k * N];
     free(acc); free(rot); free(diff);
+}
+
+/* Blind rotation two key bits per step (pair key above): with D = decomposition of ACC itself,
+ *   ACC += (X^(a1+a2) - 1) K11 (x) D + (X^a1 - 1) K10 (x) D + (X^a2 - 1) K01 (x) D
+ * which is ACC * X^(a1 s1 + a2 s2) for every value of (s1, s2).  One decomposition (one set of forward transforms
+ * in the engine) serves three GGSW products; the monomials multiply the PRODUCTS, not the decomposed input. */
+void orc_pbs_pairs(const params_t *pp, const u64 *bskp, const u64 *lut, const u64 *in, u64 *out) {
+    int n = pp->n, k = pp->k, N = pp->N, logN = ilog2(N);
+    u64 sz = (u64)(k + 1) * N, ggsw = (u64)(k + 1) * pp->bsk_l * sz;
+    u64 *acc = calloc(sz, sizeof(u64)), *prod = malloc(sizeof(u64) * sz), *rot = malloc(sizeof(u64) * N);
+    u64 *delta = malloc(sizeof(u64) * sz);
+    u64 bt = modswitch(in[n], logN);
+    poly_rotate(lut, acc + (u64)k * N, N, (2 * (u64)N - bt) & (2 * (u64)N - 1));
+    for (int q = 0; q < n / 2; q++) {
+        u64 a1 = modswitch(in[2 * q], logN), a2 = modswitch(in[2 * q + 1], logN);
+        if (a1 == 0 && a2 == 0) continue;
+        u64 e[3] = { (a1 + a2) & (2 * (u64)N - 1), a1, a2 };
+        memset(delta, 0, sizeof(u64) * sz);
+        for (int x = 0; x < 3; x++) {
+            if (e[x] == 0) continue;
+            memset(prod, 0, sizeof(u64) * sz);
+            external_product_add(pp, bskp + ((u64)q * 3 + x) * ggsw, acc, prod);
+            for (int c = 0; c <= k; c++) {
+                poly_rotate(prod + (u64)c * N, rot, N, e[x]);
+                for (int t = 0; t < N; t++)
+                    delta[(u64)c * N + t] = fadd(delta[(u64)c * N + t], fsub(rot[t], prod[(u64)c * N + t]));
+            }
+        }
+        for (u64 t = 0; t < sz; t++) acc[t] = fadd(acc[t], delta[t]);
+    }
+    for (int c = 0; c < k; c++) {
+        const u64 *A = acc + (u64)c * N; u64 *o = out + (u64)c * N;
+        o[0] = A[0];
+        for (int t = 1; t < N; t++) o[t] = fneg(A[N - t]);
+    }
+    out[(u64)k * N] = acc[(u64)k * N];
+    free(acc); free(prod); free(rot); free(delta);
 }
 
 /* ------------------------------------------------------------- keyswitch */

@@ -39,6 +39,27 @@ def test_client_keys_match_oracle(native, oracle):
         assert 0.3 < ck.S.mean() < 0.7 and ck.bsk.max() < PR.P
 
 
+def test_client_pair_key_matches_oracle_and_bootstraps(native, oracle):
+    """pair key (two key bits per blind-rotation step): same bytes as the oracle's keygen, and the oracle's pair
+    bootstrap with it decrypts to the table entry"""
+    prm = PR.TOY_1024_L1
+    ck = native.ClientKeys(prm, seed=42, threads=3, pairs=True)
+    assert ck.bsk is None and ck.bskp.shape == (prm.n // 2, 3, 2, 2, prm.N)
+    assert np.array_equal(ck.bskp, oracle.keygen_bsk_pairs(prm, 42, ck.s, ck.S))
+    table = [(5 * m + 2) % 8 for m in range(8)]
+    lut = PR.lut_polynomial([PR.encode(t, 3) for t in table], 3, prm.N)
+    for m in (0, 3, 7):
+        small = oracle.keyswitch(prm, ck.ksk, ck.encrypt([PR.encode(m, 3)])[0])
+        out = oracle.pbs_pairs(prm, ck.bskp, lut, small)
+        assert PR.decode(int(ck.phase(out)[0]), 3) == table[m]
+    odd = PR.TfheParams("odd", 41, 1, 1024, 22, 1, 4, 5, 2.0 ** 24, 2.0 ** 10)
+    try:
+        native.ClientKeys(odd, seed=1, pairs=True)
+        assert False, "expected NativeError"
+    except native.NativeError as e:
+        assert "even" in str(e)
+
+
 def test_client_encrypt_phase_match_oracle(native, oracle):
     prm = PR.TOY_1024
     ck = native.ClientKeys(prm, seed=7, evaluation_keys=False)

@@ -244,3 +244,14 @@ def test_split_overflow_is_still_detected():
     # the split lookup itself accepts the whole torus; a narrow one (x % 2, inputs 0..1) still reports leaving its range
     with pytest.raises(OverflowError):
         c.program.evaluate_clear(np.array([12] + [0] * 15, np.int64))
+
+
+def test_blind_rotation_choice_follows_configuration_and_parameter_set():
+    inputset = pairs(0, 4, (2,))
+    fn = lambda x, y: (x + y) // 2
+    comp = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"})
+    assert comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024_L1)).params.bsk_group == 2
+    assert comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024)).params.bsk_group == 1          # three levels
+    assert comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024_L1, blind_rotation="single")).params.bsk_group == 1
+    with pytest.raises(ValueError):
+        fhe.Configuration(blind_rotation="triples")

@@ -117,3 +117,18 @@ def test_split_wide_lookup_under_encryption_on_the_oracle(oracle):
         out = run_program_oracle(oracle, prog, prm, keys.bsk, keys.ksk, cts)
         dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
         assert np.array_equal(dec, fn(x, y)), (x, y)
+
+
+def test_encrypted_execution_on_the_oracle_pair_blind_rotation(oracle):
+    """same pipeline with the pair bootstrapping key (two key bits per blind-rotation step)"""
+    from oracle_exec import run_program_oracle
+    path = os.path.join(HERE, "golden", "qf_add_medium.npz")
+    z, prog = np.load(path), Program.load(path)
+    prm = PR.TOY_1024_L1
+    keys = oracle.Keys(prm, seed=3)
+    bskp = oracle.keygen_bsk_pairs(prm, 3, keys.s, keys.S)
+    x = z["golden_inputs"].astype(np.int64)[0]
+    cts = np.stack([oracle.encrypt_big(prm, keys.S, 3, i, PR.encode(int(m), prog.width)) for i, m in enumerate(x)])
+    out = run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp)
+    dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
+    assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[0])

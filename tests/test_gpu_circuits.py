@@ -13,7 +13,8 @@ from bounty_matrix_inversion_b200.fhe.program import Program
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
-TOY_FOR_WIDTH = {3: PR.TOY_1024, 4: PR.TOY_2048, 5: PR.TOY_4096, 6: PR.TOY_8192}
+# one decomposition level where a toy set has it: those circuits run the pair blind rotation (the default)
+TOY_FOR_WIDTH = {3: PR.TOY_1024, 4: PR.TOY_2048_L1, 5: PR.TOY_4096, 6: PR.TOY_8192}
 
 
 def load(name):
@@ -42,6 +43,27 @@ def test_ciphertexts_equal_oracle_execution(native, oracle):
     ref = run_program_oracle(oracle, prog, prm, circuit.keys.bsk, circuit.keys.ksk, enc.cts)
     assert np.array_equal(out.cts, ref)
     assert np.array_equal(circuit.decrypt(out), want[0])
+
+
+def test_ciphertexts_equal_oracle_execution_pair_blind_rotation(native, oracle):
+    """same program, both blind rotations: each equals the oracle's execution with the same key kind bit for bit, and
+    both decrypt to the reference's digits"""
+    from oracle_exec import run_program_oracle
+    prog, x, want = load("qf_add_medium")
+    prm = PR.TOY_1024_L1
+    pairs = fhe.Circuit.from_program(prog, prm)
+    single = fhe.Circuit.from_program(prog, prm, configuration=fhe.Configuration(blind_rotation="single"))
+    assert pairs.params.bsk_group == 2 and single.params.bsk_group == 1
+    enc = pairs.encrypt(x[1])
+    out = pairs.run(enc)
+    ref = run_program_oracle(oracle, prog, prm, None, pairs.keys.ksk, enc.cts, keys_bskp=pairs.keys.bskp)
+    assert np.array_equal(out.cts, ref)
+    assert np.array_equal(pairs.decrypt(out), want[1])
+    enc1 = single.encrypt(x[1])
+    out1 = single.run(enc1)
+    assert np.array_equal(out1.cts, run_program_oracle(oracle, prog, prm, single.keys.bsk, single.keys.ksk, enc1.cts))
+    assert np.array_equal(single.decrypt(out1), want[1])
+    assert not np.array_equal(out.cts, out1.cts)            # same message, different noise
 
 
 def test_secure_parameters_qfloat_add(native):

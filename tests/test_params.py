@@ -79,3 +79,17 @@ def test_key_sizes():
     p = PR.TOY_2048_L1
     assert p.bsk_bytes() == p.n * 2 * p.bsk_l * 2 * p.N * 8
     assert p.ksk_bytes() == p.N * p.ksk_l * (p.n + 1) * 8
+
+
+def test_pair_blind_rotation_noise_and_sets():
+    """pair key: three GGSW products per two key bits, each times a monomial minus one -> 3x the blind-rotation noise;
+    the optimizer then only picks one-level sets with an even LWE dimension"""
+    p1 = PR.optimize(4, 400.0)
+    p2 = PR.optimize(4, 400.0, bsk_group=2)
+    assert p2.bsk_group == 2 and p2.bsk_l == 1 and p2.n % 2 == 0 and p2.name.endswith("_pairs")
+    assert PR.failure_sigmas(p2, 4, 400.0) >= 6.5
+    import dataclasses
+    assert math.isclose(PR.variance_blind_rotate(dataclasses.replace(p1, bsk_group=2)), 3 * PR.variance_blind_rotate(p1))
+    assert p2.bsk_bytes() == 3 * (p2.n // 2) * 4 * p2.N * 8
+    assert PR.cost(p2) < PR.cost(dataclasses.replace(p2, bsk_group=1))
+    assert PR.for_width(4, 400.0, bsk_group=2) is PR.for_width(4, 400.0, bsk_group=2)
