@@ -1,4 +1,4 @@
-"""one PBS launch in the latency build (for ncu).  usage: pbs_lat.py <set> <count> <mode>"""
+"""one PBS launch in a chosen kernel build (for ncu).  usage: pbs_lat.py <set> <count> <mode> [pairs]"""
 import sys
 
 import numpy as np
@@ -11,9 +11,10 @@ from pbs_sweep import SETS
 
 prm = SETS[sys.argv[1]]
 count, mode = int(sys.argv[2]), int(sys.argv[3])
-keys = native.ClientKeys(prm, seed=5)
+pairs = len(sys.argv) > 4 and sys.argv[4] == "pairs"
+keys = native.ClientKeys(prm, seed=5, pairs=pairs)
 eng = native.Engine(prm, 0)
-eng.load_keys(keys.bsk, keys.ksk)
+eng.load_keys(keys.bsk, keys.ksk, bskp=keys.bskp)
 eng.set_pbs_mode(mode)
 eng.load_luts(np.stack([PR.lut_polynomial([PR.encode(t, 3) for t in range(8)], 3, prm.N)]))
 cts = np.tile(keys.encrypt([PR.encode(i % 8, 3) for i in range(8)]), (count // 8 + 1, 1))[:count]
