@@ -255,3 +255,51 @@ def test_blind_rotation_choice_follows_configuration_and_parameter_set():
     assert comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024_L1, blind_rotation="single")).params.bsk_group == 1
     with pytest.raises(ValueError):
         fhe.Configuration(blind_rotation="triples")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_wide_split_random_tables(seed):
+    """random tables on sums one bit wider than everything else: the split lowering (sign through the padding bit,
+    half-integer negacyclic / cyclic halves) must reproduce every table entry, odd differences included"""
+    r = np.random.default_rng(100 + seed)
+    terms = int(r.integers(17, 31))                       # sum of `terms` bits: 18..31 distinct values -> 5 bits
+    tables = [r.integers(-8, 8, terms + 1) for _ in range(3)]
+    nx = terms // 2
+
+    def fn(x, y):
+        s = np.sum(x) + np.sum(y)
+        out = fhe.zeros(4)
+        for i, t in enumerate(tables):
+            out[i] = fhe.univariate(lambda v, t=t: t[np.clip(v, 0, len(t) - 1)])(s)
+        out[3] = (x[0] + y[0]) % 2                         # a narrow lookup next to the wide ones
+        return out + x[:4]
+
+    shape_x, shape_y = (nx,), (terms - nx,)
+    inputset = [(r.integers(0, 2, shape_x), r.integers(0, 2, shape_y)) for _ in range(60)]
+    inputset += [(np.zeros(shape_x, np.int64), np.zeros(shape_y, np.int64)), (np.ones(shape_x, np.int64), np.ones(shape_y, np.int64))]
+    comp = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"})
+    split = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, split_wide=True, split_guard=0))
+    wide = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, split_wide=False))
+    assert wide.program.width == 5 and split.program.width == 4 and split.statistics["split_lookups"] >= 1
+    for total in range(terms + 1):                          # every reachable sum
+        bits = np.array([1] * total + [0] * (terms - total))
+        x, y = bits[:nx], bits[nx:]
+        want = fn(x, y)
+        assert np.array_equal(split.simulate(x, y), want), total
+        assert np.array_equal(wide.simulate(x, y), want), total
+
+
+def test_clear_evaluation_is_modular_like_the_ciphertexts():
+    """table outputs are stored reduced mod 2^(W+1); sums of them that wrap are still right at the next lookup"""
+    r = np.random.default_rng(5)
+
+    def fn(x, y):
+        a = fhe.univariate(lambda v: v + 16)(x[0])          # 16..19: outside a 3-bit message space
+        b = fhe.univariate(lambda v: v % 2 - 16)(y[0])
+        return (a + b + x[0]) // 2                          # the sum is small again: 0..7
+
+    inputset = [(r.integers(0, 4, 1), r.integers(0, 4, 1)) for _ in range(60)]
+    c = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"}).compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
+    assert c.program.width == 3 and np.abs(c.program.tables).max() <= 1 << c.program.width
+    for x, y in inputset:
+        assert np.array_equal(c.simulate(x, y), fn(x, y))
