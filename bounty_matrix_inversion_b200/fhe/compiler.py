@@ -18,7 +18,7 @@ class Configuration:
     """accepts Concrete's keyword options; the ones this engine understands:
     tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, seed, device,
     multiplication ("auto" | "quarter_square", see tracing.Trace),
-    split_wide ("auto" | True | False) and split_guard (see program.lower),
+    split_wide ("auto" | True | False), split_guard and collapse_borrows (see program.lower),
     blind_rotation ("pairs" | "single"): two key bits per bootstrap step with the pair key (default wherever the
     parameter set has one decomposition level and an even LWE dimension), or one GGSW per key bit"""
 
@@ -32,6 +32,7 @@ class Configuration:
         self.multiplication = options.get("multiplication", "auto")
         self.split_wide = options.get("split_wide", "auto")
         self.split_guard = options.get("split_guard")
+        self.collapse_borrows = options.get("collapse_borrows", True)
         self.blind_rotation = options.get("blind_rotation", "pairs")
         if self.blind_rotation not in ("pairs", "single"):
             raise ValueError("blind_rotation must be 'pairs' or 'single'")
@@ -102,7 +103,7 @@ class Compiler:
         t1 = time.time()
         n_out = len(flat_out)
         prog = lower(trace, flat_out, (n_out,), slack_bits=cfg.slack_bits, split_wide=cfg.split_wide,
-                     split_guard=cfg.split_guard)
+                     split_guard=cfg.split_guard, collapse_borrows=cfg.collapse_borrows)
         t2 = time.time()
         prm = None if cfg.tfhe_params == "deferred" else (cfg.tfhe_params or _select_params(prog, cfg))
         prog.stats.update(trace_s=round(t1 - t0, 3), lower_s=round(t2 - t1, 3), params_s=round(time.time() - t2, 3))

@@ -168,6 +168,23 @@ class Program:
         return (out[0], bad[0]) if single else (out, bad)
 
 
+_PROBE = np.arange(-70, 71, dtype=np.int64)
+
+
+def _lt0_scale(fn) -> int:
+    """c if the lookup function is x -> c [x < 0] with c != 0, else 0 (decided on values: the tracer keeps functions
+    opaque, and it folds a constant factor such as the `p *` of `temp + p * borrow` into the table)"""
+    try:
+        v = np.asarray(fn(_PROBE))
+    except Exception:
+        return 0
+    if v.shape != _PROBE.shape:
+        return 0
+    v = v.astype(np.int64)
+    c = int(v[0])
+    return c if c and np.array_equal(v, c * (_PROBE < 0)) else 0
+
+
 def _narrowing_pays(wide: "Program", narrow: "Program") -> bool:
     """one bit of width doubles the polynomial size: bootstrap work grows 2 (W + 7) / (W + 6)-fold (transform
     butterflies), the latency of one level about 1.6-fold (measured)"""
@@ -187,19 +204,26 @@ def _csr_apply(row_ptr, idx, coef, konst, vals):
 
 
 # ------------------------------------------------------------------ lowering
-def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, split_wide="auto", split_guard=None) -> Program:
+def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, split_wide="auto", split_guard=None,
+          collapse_borrows: bool = True) -> Program:
     """trace: fhe.tracing.Trace after the circuit function ran; outputs: flat list of scalars
     (ints / Aff) the function returned.
     split_wide: True lowers the lookups that alone need the top bit of width into three narrower bootstraps (module
     docstring); False never does; "auto" does when the narrower width halves the polynomial size (W >= 5), the wide
     lookups are a minority, and the narrowed program is cheaper both in total bootstrap work and along its critical
     path (`_narrowing_pays`).  split_guard: spare table entries required either side of a lookup's observed range in a narrowed
-    program, lookups with less are split as well (default 2^W / 4)."""
+    program, lookups with less are split as well (default 2^W / 4).
+    collapse_borrows: a borrow chain  b' = [A - b < 0],  b = [S < 0]  (the reference's digit-by-digit subtraction,
+    base_p_arrays.py:119-121, 70 % of an inversion's critical path) is rewritten  b' = [M A + S < 0]  with
+    M = max(-min S, max S + 1): the same bit for every integer A as long as S stays inside the bounds M was derived
+    from, and no longer dependent on b -- so two digits resolve per level.  The bounds are the range S showed on the
+    inputset widened by one either side where the message space allows (the same assumption every lookup window makes;
+    DESIGN.md section 3 measures what it costs on fresh inputs), and the rewrite is only done where M A + S fits."""
     if split_wide == "auto":
-        wide = lower(trace, outputs, out_shape, slack_bits, min_width, False)
+        wide = lower(trace, outputs, out_shape, slack_bits, min_width, False, None, collapse_borrows)
         if wide.width - slack_bits < 5 or wide.stats["top_width_lookups"] * 10 > wide.stats["live_lookups"]:
             return wide
-        narrow = lower(trace, outputs, out_shape, slack_bits, min_width, True, split_guard)
+        narrow = lower(trace, outputs, out_shape, slack_bits, min_width, True, split_guard, collapse_borrows)
         return narrow if narrow.width < wide.width and _narrowing_pays(wide, narrow) else wide
     n_in = trace.n_inputs
     jobs = trace.jobs
@@ -243,7 +267,8 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     subst = {}                 # traced base -> {representative base: coefficient} where they differ
     job_info = {}              # representative base -> (src key, table id)
     full_keys = set()          # keyswitch rows that use the padding bit on purpose
-    state = {"nu2": 1, "next": n_in + len(jobs), "split": 0}
+    state = {"nu2": 1, "next": n_in + len(jobs), "split": 0, "collapsed": 0}
+    lt0_src = {}               # representative base of a lookup [S < 0] -> (terms of S, constant of S, observed min, max)
 
     def resolve(src):
         terms = {}
@@ -281,16 +306,56 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         state["nu2"] = max(state["nu2"], sum(c * c for _b, c in key[0]))
         return base
 
+    def _collapse_borrow(jb, terms, scale):
+        g2 = jb.group
+        for b1, c1 in terms.items():
+            if c1 != -1 or b1 not in lt0_src:
+                continue
+            s_terms, s_const, s_lo, s_hi = lt0_src[b1]
+            a_terms = {b: c for b, c in terms.items() if b != b1}
+            a_lo, a_hi = g2.lo, g2.hi + 1                   # A = (A - b) + b with b in {0, 1}
+            for margin in (1, 0):                           # tolerate S one step outside what the inputset showed, if it fits
+                M = max(-(s_lo - margin), s_hi + margin + 1, 1)
+                t_lo, t_hi = M * a_lo + s_lo - margin, M * a_hi + s_hi + margin
+                if t_hi - t_lo + 1 <= size:
+                    break
+            else:
+                continue
+            t_terms = dict(s_terms)
+            for b, c in a_terms.items():
+                v = t_terms.get(b, 0) + M * c
+                if v:
+                    t_terms[b] = v
+                else:
+                    t_terms.pop(b, None)
+            t_const = M * jb.const + s_const
+            offset = (size - (t_hi - t_lo + 1)) // 2 - t_lo
+            key = (tuple(sorted(t_terms.items())), t_const + offset)
+            rep = add_lookup(jb.base, key, scale * (dom - offset < 0))
+            if rep != jb.base:
+                subst[jb.base] = {rep: 1}
+            if scale == 1:
+                lt0_src.setdefault(rep, (t_terms, t_const, t_lo, t_hi))
+            state["collapsed"] += 1
+            return True
+        return False
+
     for j in np.flatnonzero(live):        # jobs are in creation (topological) order
         jb = jobs[j]
         g = jb.group
         terms = resolve(jb.terms)
+        lt0 = _lt0_scale(jb.fn) if collapse_borrows else 0
+        if lt0 and _collapse_borrow(jb, terms, lt0):
+            continue
         if (g.hi - g.lo + 1) + 2 * guard <= size or not narrowed:
             offset = (size - (g.hi - g.lo + 1)) // 2 - g.lo           # centre [lo, hi] in [0, 2^W)
             key = (tuple(sorted(terms.items())), jb.const + offset)
-            rep = add_lookup(jb.base, key, jb.fn(dom - offset))
+            raw = np.broadcast_to(np.asarray(jb.fn(dom - offset), dtype=np.int64), (size,))
+            rep = add_lookup(jb.base, key, raw)
             if rep != jb.base:
                 subst[jb.base] = {rep: 1}
+            if lt0 == 1:
+                lt0_src.setdefault(rep, (dict(terms), jb.const, g.lo, g.hi))
             continue
         # one bit too wide: sign through the padding bit, then negacyclic + cyclic halves (module docstring)
         assert bits[int(j)] <= W + 1, "lookup more than one bit wider than the program width"
@@ -392,5 +457,6 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
                    table_half=np.asarray(table_half, bool) if tables else None)
     prog.stats = {"traced_lookups": len(jobs), "live_lookups": int(live.sum()), "pbs": prog.n_pbs, "keyswitches": prog.n_ks,
                   "levels": n_levels, "tables": len(tables), "slots": n_slots, "width": W, "nu2": int(nu2),
-                  "max_level_pbs": max((len(l.job_ks) for l in levels), default=0), "split_lookups": state["split"], "top_width_lookups": n_top}
+                  "max_level_pbs": max((len(l.job_ks) for l in levels), default=0), "split_lookups": state["split"], "top_width_lookups": n_top,
+                  "collapsed_borrows": state["collapsed"]}
     return prog

@@ -45,6 +45,7 @@ class Trace:
         self.n_inputs = 0
         self.jobs = []          # Job objects, index = base_id - n_inputs once inputs are frozen
         self.n_bases = 0
+        self.input_ranges = []  # (min, max) of every input over the inputset
 
     def __enter__(self):
         if current() is not None:
@@ -60,7 +61,9 @@ class Trace:
         self.n_bases += 1
         self.n_inputs += 1
         assert not self.jobs, "inputs must be declared before any lookup"
-        return Aff({base: 1}, 0, np.asarray(vals, dtype=np.int64))
+        vals = np.asarray(vals, dtype=np.int64)
+        self.input_ranges.append((int(vals.min()), int(vals.max())))
+        return Aff({base: 1}, 0, vals)
 
     def new_lookup(self, src: "Aff", fn, group: "Group", vals):
         base = self.n_bases

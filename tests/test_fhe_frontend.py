@@ -303,3 +303,54 @@ def test_clear_evaluation_is_modular_like_the_ciphertexts():
     assert c.program.width == 3 and np.abs(c.program.tables).max() <= 1 << c.program.width
     for x, y in inputset:
         assert np.array_equal(c.simulate(x, y), fn(x, y))
+
+
+# ---------------------------------------------------------------- borrow-chain collapse (program.lower docstring)
+def _subtract_digits(a, b):
+    """schoolbook base-2 subtraction a - b, least significant digit last; returns digits and the final borrow"""
+    out = fhe.zeros(a.size + 1)
+    borrow = 0
+    d = a - b
+    for i in range(a.size):
+        t = d[-i - 1] - borrow
+        borrow = t < 0
+        out[-i - 2] = t + 2 * borrow
+    out[-1] = borrow
+    return out
+
+
+def test_borrow_chain_resolves_two_digits_per_level():
+    n = 8
+    r = np.random.default_rng(21)
+    inputset = [(r.integers(0, 2, n), r.integers(0, 2, n)) for _ in range(80)]
+    comp = fhe.Compiler(_subtract_digits, {"a": "encrypted", "b": "encrypted"})
+    narrow = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
+    assert narrow.program.width == 2 and narrow.statistics["collapsed_borrows"] == 0      # no room in a 2-bit message space
+    plain = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, collapse_borrows=False, slack_bits=2))
+    fast = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, slack_bits=2))      # 4 bits, like the reference's circuits
+    assert plain.statistics["levels"] == n and plain.statistics["collapsed_borrows"] == 0
+    # per digit the tracer emits [t < 0] (the next digit's borrow) and 2 [t < 0] (folded into this digit): both collapse
+    assert fast.statistics["levels"] == n // 2 and fast.statistics["collapsed_borrows"] == n
+    assert fast.statistics["pbs"] == plain.statistics["pbs"] == 2 * n and fast.program.width == plain.program.width
+    # every pair of 8-bit numbers' worth of digit patterns that matter: all 2^16 inputs, vectorised
+    grid = np.array([[(v >> k) & 1 for k in range(2 * n)] for v in range(1 << (2 * n))], dtype=np.int64)
+    want = np.stack([np.asarray(_subtract_digits(row[:n], row[n:])) for row in grid[:: 257]])
+    assert np.array_equal(fast.program.evaluate_clear(grid[:: 257]), want)
+    assert np.array_equal(fast.program.evaluate_clear(grid), plain.program.evaluate_clear(grid))
+
+
+def test_borrow_collapse_leaves_other_threshold_chains_alone():
+    """[A + b < 0], [A - 2 b < 0] and [A - f(S) < 0] with f not a sign test are not the borrow pattern"""
+    r = np.random.default_rng(22)
+
+    def fn(x, y):
+        b = x[0] - y[0] < 0
+        out = fhe.zeros(3)
+        out[0] = (x[1] - y[1] + b) < 0
+        out[1] = (x[2] - y[2] - 2 * b) < 0
+        out[2] = (x[3] - y[3] - (x[0] - y[0] < 1)) < 0
+        return out
+
+    inputset = [(r.integers(0, 3, 4), r.integers(0, 3, 4)) for _ in range(80)]
+    c = check(fn, inputset)
+    assert c.statistics["collapsed_borrows"] == 0 and c.statistics["levels"] == 2

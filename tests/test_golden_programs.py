@@ -132,3 +132,20 @@ def test_encrypted_execution_on_the_oracle_pair_blind_rotation(oracle):
     out = run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp)
     dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
     assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[0])
+
+
+def test_division_with_collapsed_borrow_chains_under_encryption_on_the_oracle(oracle):
+    """the reference's QFloat division (long division = nested borrow chains, two digits per level after the
+    collapse) executed on encrypted data by the CPU oracle decrypts to the reference's digits"""
+    from oracle_exec import run_program_oracle
+    path = os.path.join(HERE, "golden", "qf_div_medium.npz")
+    z, prog = np.load(path), Program.load(path)
+    assert prog.stats["collapsed_borrows"] > 500 and prog.stats["levels"] < 600
+    prm = PR.TOY_1024_L1
+    keys = oracle.Keys(prm, seed=9)
+    for lane in (0, 5):
+        x = z["golden_inputs"].astype(np.int64)[lane]
+        cts = np.stack([oracle.encrypt_big(prm, keys.S, 9, 1000 * lane + i, PR.encode(int(m), prog.width)) for i, m in enumerate(x)])
+        out = run_program_oracle(oracle, prog, prm, keys.bsk, keys.ksk, cts)
+        dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
+        assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[lane]), lane
