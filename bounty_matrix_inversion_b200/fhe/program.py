@@ -64,6 +64,7 @@ class Program:
     nu2: int                 # largest squared 2-norm of a lookup input's linear combination
     stats: dict = field(default_factory=dict)
     table_half: np.ndarray = None   # [n_luts] bool: table holds 2x its values (half-integer outputs)
+    debug: dict = None
 
     def __post_init__(self):
         if self.table_half is None:
@@ -269,6 +270,13 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     full_keys = set()          # keyswitch rows that use the padding bit on purpose
     state = {"nu2": 1, "next": n_in + len(jobs), "split": 0, "collapsed": 0}
     lt0_src = {}               # representative base of a lookup [S < 0] -> (terms of S, constant of S, observed min, max)
+    # A borrow chain is the same digit recurrence at every position, but a given position may have shown only part of
+    # its range on the inputset (a leading digit that happened to be 0 in all samples).  Every borrow source is
+    # therefore assumed to span what borrow sources span ANYWHERE in the program (for base-2 digits: [-2, 1]).
+    scales = {int(j): _lt0_scale(jobs[j].fn) for j in np.flatnonzero(live)} if collapse_borrows else {}
+    lt0_jobs = [jobs[j] for j, c in scales.items() if c]
+    span_lo = min((jb.group.lo for jb in lt0_jobs), default=0)
+    span_hi = max((jb.group.hi for jb in lt0_jobs), default=0)
 
     def resolve(src):
         terms = {}
@@ -313,7 +321,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
                 continue
             s_terms, s_const, s_lo, s_hi = lt0_src[b1]
             a_terms = {b: c for b, c in terms.items() if b != b1}
-            a_lo, a_hi = g2.lo, g2.hi + 1                   # A = (A - b) + b with b in {0, 1}
+            a_lo, a_hi = min(g2.lo, span_lo), max(g2.hi, span_hi) + 1       # A = (A - b) + b with b in {0, 1}
             for margin in (1, 0):                           # tolerate S one step outside what the inputset showed, if it fits
                 M = max(-(s_lo - margin), s_hi + margin + 1, 1)
                 t_lo, t_hi = M * a_lo + s_lo - margin, M * a_hi + s_hi + margin
@@ -344,7 +352,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         jb = jobs[j]
         g = jb.group
         terms = resolve(jb.terms)
-        lt0 = _lt0_scale(jb.fn) if collapse_borrows else 0
+        lt0 = scales.get(int(j), 0)
         if lt0 and _collapse_borrow(jb, terms, lt0):
             continue
         if (g.hi - g.lo + 1) + 2 * guard <= size or not narrowed:
@@ -355,7 +363,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
             if rep != jb.base:
                 subst[jb.base] = {rep: 1}
             if lt0 == 1:
-                lt0_src.setdefault(rep, (dict(terms), jb.const, g.lo, g.hi))
+                lt0_src.setdefault(rep, (dict(terms), jb.const, min(g.lo, span_lo), max(g.hi, span_hi)))
             continue
         # one bit too wide: sign through the padding bit, then negacyclic + cyclic halves (module docstring)
         assert bits[int(j)] <= W + 1, "lookup more than one bit wider than the program width"
@@ -459,4 +467,5 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
                   "levels": n_levels, "tables": len(tables), "slots": n_slots, "width": W, "nu2": int(nu2),
                   "max_level_pbs": max((len(l.job_ks) for l in levels), default=0), "split_lookups": state["split"], "top_width_lookups": n_top,
                   "collapsed_borrows": state["collapsed"]}
+    prog.debug = {"level_of": level_of, "subst": subst, "job_info": job_info}      # for scripts/critical_path.py; not saved
     return prog
