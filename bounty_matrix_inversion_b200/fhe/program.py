@@ -217,9 +217,10 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     collapse_borrows: a borrow chain  b' = [A - b < 0],  b = [S < 0]  (the reference's digit-by-digit subtraction,
     base_p_arrays.py:119-121, 70 % of an inversion's critical path) is rewritten  b' = [M A + S < 0]  with
     M = max(-min S, max S + 1): the same bit for every integer A as long as S stays inside the bounds M was derived
-    from, and no longer dependent on b -- so two digits resolve per level.  The bounds are the range S showed on the
-    inputset widened by one either side where the message space allows (the same assumption every lookup window makes;
-    DESIGN.md section 3 measures what it costs on fresh inputs), and the rewrite is only done where M A + S fits."""
+    from, and no longer dependent on b -- so several digits resolve per level (True: as many as fit the message space,
+    three base-2 digits in 4 bits; 2: two, with one step of slack on S where it fits; False: none).  The bounds are what
+    borrow sources and digit differences span ANYWHERE in the program on the inputset (the recurrence is the same at
+    every digit position; a single position may have shown less), and the rewrite is only done where M A + S fits."""
     if split_wide == "auto":
         wide = lower(trace, outputs, out_shape, slack_bits, min_width, False, None, collapse_borrows)
         if wide.width - slack_bits < 5 or wide.stats["top_width_lookups"] * 10 > wide.stats["live_lookups"]:
@@ -277,6 +278,16 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     lt0_jobs = [jobs[j] for j, c in scales.items() if c]
     span_lo = min((jb.group.lo for jb in lt0_jobs), default=0)
     span_hi = max((jb.group.hi for jb in lt0_jobs), default=0)
+    # ... and every digit difference A what digit differences span anywhere (A = source + borrow, per sample)
+    a_span = [0, 0]
+    for jb in lt0_jobs:
+        for b, c in jb.terms.items():
+            if c == -1 and b >= n_in and scales.get(b - n_in) == 1:
+                a = jb.src_vals.astype(np.int64) + jobs[b - n_in].out_vals
+                a_span = [min(a_span[0], int(a.min())), max(a_span[1], int(a.max()))]
+    # True: as many digits per level as the message space holds with the spans taken exactly (three base-2 digits in
+    # 4 bits); 2: two digits, and the previous source may leave its span by one where that still fits
+    margins = (1, 0) if collapse_borrows == 2 and collapse_borrows is not True else (0,)
 
     def resolve(src):
         terms = {}
@@ -315,14 +326,13 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         return base
 
     def _collapse_borrow(jb, terms, scale):
-        g2 = jb.group
         for b1, c1 in terms.items():
             if c1 != -1 or b1 not in lt0_src:
                 continue
             s_terms, s_const, s_lo, s_hi = lt0_src[b1]
             a_terms = {b: c for b, c in terms.items() if b != b1}
-            a_lo, a_hi = min(g2.lo, span_lo), max(g2.hi, span_hi) + 1       # A = (A - b) + b with b in {0, 1}
-            for margin in (1, 0):                           # tolerate S one step outside what the inputset showed, if it fits
+            a_lo, a_hi = a_span
+            for margin in margins:                          # tolerate S one step outside its span, if it fits
                 M = max(-(s_lo - margin), s_hi + margin + 1, 1)
                 t_lo, t_hi = M * a_lo + s_lo - margin, M * a_hi + s_hi + margin
                 if t_hi - t_lo + 1 <= size:

@@ -69,7 +69,7 @@ class Trace:
         base = self.n_bases
         self.n_bases += 1
         group.see(src.vals)
-        self.jobs.append(Job(base, src.terms, src.const, fn, group))
+        self.jobs.append(Job(base, src.terms, src.const, fn, group, src.vals, vals))
         return Aff({base: 1}, 0, vals)
 
 
@@ -95,10 +95,17 @@ class Group:
 
 
 class Job:
-    __slots__ = ("base", "terms", "const", "fn", "group")
+    __slots__ = ("base", "terms", "const", "fn", "group", "src_vals", "out_vals")
 
-    def __init__(self, base, terms, const, fn, group):
+    def __init__(self, base, terms, const, fn, group, src_vals, out_vals):
         self.base, self.terms, self.const, self.fn, self.group = base, terms, const, fn, group
+        # source and result on every inputset sample (the lowering derives ranges of combinations from them)
+        self.src_vals, self.out_vals = _compact(src_vals), _compact(out_vals)
+
+
+def _compact(vals):
+    v = np.asarray(vals)
+    return v.astype(np.int16) if v.size and -32768 <= v.min() and v.max() <= 32767 else v.astype(np.int64)
 
 
 # ------------------------------------------------------------------ scalars

@@ -319,24 +319,26 @@ def _subtract_digits(a, b):
     return out
 
 
-def test_borrow_chain_resolves_two_digits_per_level():
+def test_borrow_chain_resolves_several_digits_per_level():
     n = 8
     r = np.random.default_rng(21)
     inputset = [(r.integers(0, 2, n), r.integers(0, 2, n)) for _ in range(80)]
     comp = fhe.Compiler(_subtract_digits, {"a": "encrypted", "b": "encrypted"})
     narrow = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024))
     assert narrow.program.width == 2 and narrow.statistics["collapsed_borrows"] == 0      # no room in a 2-bit message space
-    plain = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, collapse_borrows=False, slack_bits=2))
-    fast = comp.compile(inputset, fhe.Configuration(tfhe_params=PR.TOY_1024, slack_bits=2))      # 4 bits, like the reference's circuits
-    assert plain.statistics["levels"] == n and plain.statistics["collapsed_borrows"] == 0
+    cfg = lambda **kw: fhe.Configuration(tfhe_params=PR.TOY_1024, slack_bits=2, **kw)      # 4 bits, like the reference's circuits
+    plain, two, three = (comp.compile(inputset, cfg(collapse_borrows=c)) for c in (False, 2, True))
     # per digit the tracer emits [t < 0] (the next digit's borrow) and 2 [t < 0] (folded into this digit): both collapse
-    assert fast.statistics["levels"] == n // 2 and fast.statistics["collapsed_borrows"] == n
-    assert fast.statistics["pbs"] == plain.statistics["pbs"] == 2 * n and fast.program.width == plain.program.width
-    # every pair of 8-bit numbers' worth of digit patterns that matter: all 2^16 inputs, vectorised
+    assert [c.statistics["levels"] for c in (plain, two, three)] == [n, n // 2, (n + 2) // 3]
+    assert [c.statistics["collapsed_borrows"] for c in (plain, two, three)] == [0, n, 10]
+    assert all(c.statistics["pbs"] == 2 * n and c.program.width == 4 for c in (plain, two, three))
+    # all 2^16 digit patterns, vectorised: identical to the uncollapsed program, and to the function itself on a sample
     grid = np.array([[(v >> k) & 1 for k in range(2 * n)] for v in range(1 << (2 * n))], dtype=np.int64)
     want = np.stack([np.asarray(_subtract_digits(row[:n], row[n:])) for row in grid[:: 257]])
-    assert np.array_equal(fast.program.evaluate_clear(grid[:: 257]), want)
-    assert np.array_equal(fast.program.evaluate_clear(grid), plain.program.evaluate_clear(grid))
+    base = plain.program.evaluate_clear(grid)
+    for c in (two, three):
+        assert np.array_equal(c.program.evaluate_clear(grid[:: 257]), want)
+        assert np.array_equal(c.program.evaluate_clear(grid), base)
 
 
 def test_borrow_collapse_leaves_other_threshold_chains_alone():
