@@ -270,6 +270,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     job_info = {}              # representative base -> (src key, table id)
     full_keys = set()          # keyswitch rows that use the padding bit on purpose
     state = {"nu2": 1, "next": n_in + len(jobs), "split": 0, "collapsed": 0}
+    split_of = {}              # helper lookup of a split -> the traced lookup it serves (debug only)
     lt0_src = {}               # representative base of a lookup [S < 0] -> (terms of S, constant of S, observed min, max)
     # A borrow chain is the same digit recurrence at every position, but a given position may have shown only part of
     # its range on the inputset (a leading digit that happened to be 0 in all samples).  Every borrow source is
@@ -389,6 +390,8 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         key_low = (tuple(sorted(low.items())), jb.const + offset - size // 2)
         cyc = add_lookup(None, key_low, f[:size] + f[size:], half=True)
         subst[jb.base] = {neg: 1, cyc: 1}
+        for helper in (sgn, neg, cyc):
+            split_of.setdefault(helper, jb.base)
         state["split"] += 1
     nu2 = state["nu2"]
 
@@ -477,5 +480,5 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
                   "levels": n_levels, "tables": len(tables), "slots": n_slots, "width": W, "nu2": int(nu2),
                   "max_level_pbs": max((len(l.job_ks) for l in levels), default=0), "split_lookups": state["split"], "top_width_lookups": n_top,
                   "collapsed_borrows": state["collapsed"]}
-    prog.debug = {"level_of": level_of, "subst": subst, "job_info": job_info}      # for scripts/critical_path.py; not saved
+    prog.debug = {"level_of": level_of, "subst": subst, "job_info": job_info, "split_of": split_of}      # for scripts/critical_path.py; not saved
     return prog

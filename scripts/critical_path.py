@@ -35,6 +35,8 @@ for jb in trace.jobs:                      # representative -> site of the first
     rep = jb.base if sub is None else (next(iter(sub)) if len(sub) == 1 else None)
     if rep is not None:
         site_of.setdefault(rep, sites[jb.base])
+for helper, base in prog.debug["split_of"].items():
+    site_of.setdefault(helper, "split: " + sites[base])
 end = max(level_of, key=level_of.get)
 path, b = [], end
 while b is not None:
