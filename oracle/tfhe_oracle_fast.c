@@ -45,8 +45,11 @@ typedef struct {
     params_t pp;
     int logN;
     u64 *tw, *twi;      /* psi^{brv(i)}, psi^{-brv(i)} */
-    u64 *bsk_hat;       /* [n][rows][k+1][N], transform domain, pre-scaled by 1/N */
+    u64 *bsk_hat;       /* [n][rows][k+1][N], transform domain, pre-scaled by 1/N; pair key: [n/2][3][rows][k+1][N] */
     const u64 *ksk;     /* borrowed */
+    int pairs;          /* blind rotation two key bits per step with the pair key (tfhe_oracle.c orc_pbs_pairs) */
+    u64 *pw;            /* [2N] psi^t */
+    int *expo;          /* [N] transform slot u evaluates at psi^expo[u] */
 } ctx_t;
 
 static void fwd(const ctx_t *c, u64 *a) {
@@ -70,14 +73,27 @@ static void inv(const ctx_t *c, u64 *a) {   /* unscaled: the 1/N lives in bsk_ha
     }
 }
 
-void *orcf_create(const params_t *pp, const u64 *bsk, const u64 *ksk) {
+static void *create(const params_t *pp, const u64 *bsk, const u64 *ksk, int pairs) {
     ctx_t *c = calloc(1, sizeof(ctx_t));
-    c->pp = *pp; c->logN = ilog2(pp->N); c->ksk = ksk;
+    c->pp = *pp; c->logN = ilog2(pp->N); c->ksk = ksk; c->pairs = pairs;
     int N = pp->N, L = c->logN;
     u64 psi = fpow(7, (P - 1) / (2 * (u64)N)), psii = fpow(psi, P - 2);
     c->tw = malloc(sizeof(u64) * N); c->twi = malloc(sizeof(u64) * N);
     for (int i = 0; i < N; i++) { c->tw[i] = fpow(psi, brv(i, L)); c->twi[i] = fpow(psii, brv(i, L)); }
-    u64 polys = (u64)pp->n * (pp->k + 1) * pp->bsk_l * (pp->k + 1);
+    if (pairs) {
+        /* evaluation point of every transform slot = transform of the monomial X; its discrete log by table */
+        c->pw = malloc(sizeof(u64) * 2 * N); c->expo = malloc(sizeof(int) * N);
+        c->pw[0] = 1;
+        for (int t = 1; t < 2 * N; t++) c->pw[t] = fmul(c->pw[t - 1], psi);
+        u64 *x = calloc(N, sizeof(u64)); x[1] = 1;
+        fwd(c, x);
+        for (int u = 0; u < N; u++) {
+            c->expo[u] = -1;
+            for (int t = 1; t < 2 * N; t += 2) if (c->pw[t] == x[u]) { c->expo[u] = t; break; }
+        }
+        free(x);
+    }
+    u64 polys = (u64)(pairs ? 3 * (pp->n / 2) : pp->n) * (pp->k + 1) * pp->bsk_l * (pp->k + 1);
     c->bsk_hat = malloc(sizeof(u64) * polys * N);
     u64 ninv = fpow((u64)N, P - 2);
     for (u64 q = 0; q < polys; q++) {
@@ -87,12 +103,66 @@ void *orcf_create(const params_t *pp, const u64 *bsk, const u64 *ksk) {
     }
     return c;
 }
-void orcf_destroy(void *h) { ctx_t *c = h; free(c->tw); free(c->twi); free(c->bsk_hat); free(c); }
+void *orcf_create(const params_t *pp, const u64 *bsk, const u64 *ksk) { return create(pp, bsk, ksk, 0); }
+void *orcf_create_pairs(const params_t *pp, const u64 *bskp, const u64 *ksk) { return create(pp, bskp, ksk, 1); }
+void orcf_destroy(void *h) { ctx_t *c = h; free(c->tw); free(c->twi); free(c->bsk_hat); free(c->pw); free(c->expo); free(c); }
 
 static inline u64 modswitch(u64 x, int logN) { return (((x >> (62 - logN)) + 1) >> 1) & ((2ULL << logN) - 1); }
 
+/* pair blind rotation: per step the accumulator itself is decomposed and transformed once; the three GGSWs of the
+ * pair enter as  m11 K11 + m10 K10 + m01 K01  with the monomials X^e - 1 evaluated per slot (psi^(e r) - 1) */
+static void pbs_pairs(const ctx_t *c, const u64 *lut, const u64 *in, u64 *out) {
+    const params_t *pp = &c->pp;
+    int n = pp->n, k = pp->k, N = pp->N, l = pp->bsk_l, bl = pp->bsk_bl, tot = bl * l;
+    u64 sz = (u64)(k + 1) * N, B = 1ULL << bl, twoN = 2 * (u64)N, ggsw = (u64)(k + 1) * l * sz;
+    u64 *acc = calloc(sz, sizeof(u64)), *rnd = malloc(sizeof(u64) * sz);
+    u64 *dig = malloc(sizeof(u64) * N), *sum = malloc(sizeof(u64) * sz), *m = malloc(sizeof(u64) * 3 * N);
+    u64 rb = (twoN - modswitch(in[n], c->logN)) & (twoN - 1);
+    for (int t = 0; t < N; t++) { u64 u = ((u64)t + twoN - rb) & (twoN - 1); acc[(u64)k * N + t] = u < (u64)N ? lut[u] : fneg(lut[u - N]); }
+    for (int q = 0; q < n / 2; q++) {
+        u64 a1 = modswitch(in[2 * q], c->logN), a2 = modswitch(in[2 * q + 1], c->logN);
+        if (!a1 && !a2) continue;
+        for (int t = 0; t < N; t++) {
+            u64 p10 = c->pw[(a1 * (u64)c->expo[t]) & (twoN - 1)], p01 = c->pw[(a2 * (u64)c->expo[t]) & (twoN - 1)];
+            m[t] = fsub(fmul(p10, p01), 1); m[N + t] = fsub(p10, 1); m[2 * N + t] = fsub(p01, 1);
+        }
+        for (u64 t = 0; t < sz; t++) { u64 r = ((acc[t] >> (63 - tot)) + 1) >> 1; if (tot < 64) r &= (1ULL << tot) - 1; rnd[t] = r; }
+        memset(sum, 0, sizeof(u64) * sz);
+        const u64 *g = c->bsk_hat + (u64)q * 3 * ggsw;
+        for (int j = l; j >= 1; j--) for (int cc = 0; cc <= k; cc++) {
+            u64 *r = rnd + (u64)cc * N;
+            for (int t = 0; t < N; t++) {
+                u64 d = r[t] & (B - 1); r[t] >>= bl;
+                if (d >= B / 2) { dig[t] = P - (B - d); r[t] += 1; } else dig[t] = d;
+            }
+            fwd(c, dig);
+            u64 row = (u64)(cc * l + (j - 1)) * sz;
+            for (int o = 0; o <= k; o++) {
+                u64 *s = sum + (u64)o * N;
+                const u64 *b11 = g + row + (u64)o * N, *b10 = b11 + ggsw, *b01 = b10 + ggsw;
+                for (int t = 0; t < N; t++) {
+                    u64 key = fadd(fadd(fmul(m[t], b11[t]), fmul(m[N + t], b10[t])), fmul(m[2 * N + t], b01[t]));
+                    s[t] = fadd(s[t], fmul(dig[t], key));
+                }
+            }
+        }
+        for (int o = 0; o <= k; o++) {
+            inv(c, sum + (u64)o * N);
+            for (int t = 0; t < N; t++) acc[(u64)o * N + t] = fadd(acc[(u64)o * N + t], sum[(u64)o * N + t]);
+        }
+    }
+    for (int cc = 0; cc < k; cc++) {
+        const u64 *A = acc + (u64)cc * N; u64 *o = out + (u64)cc * N;
+        o[0] = A[0];
+        for (int t = 1; t < N; t++) o[t] = fneg(A[N - t]);
+    }
+    out[(u64)k * N] = acc[(u64)k * N];
+    free(acc); free(rnd); free(dig); free(sum); free(m);
+}
+
 void orcf_pbs(void *h, const u64 *lut, const u64 *in, u64 *out) {
     const ctx_t *c = h; const params_t *pp = &c->pp;
+    if (c->pairs) { pbs_pairs(c, lut, in, out); return; }
     int n = pp->n, k = pp->k, N = pp->N, l = pp->bsk_l, bl = pp->bsk_bl, tot = bl * l;
     u64 sz = (u64)(k + 1) * N, B = 1ULL << bl, twoN = 2 * (u64)N;
     u64 *acc = calloc(sz, sizeof(u64)), *rnd = malloc(sizeof(u64) * sz);

@@ -5,11 +5,12 @@ import numpy as np
 from bounty_matrix_inversion_b200 import params as PR
 
 
-def run_program_oracle(orc, prog, prm, keys_bsk, keys_ksk, input_cts, threads=8, keys_bskp=None):
+def run_program_oracle(orc, prog, prm, keys_bsk, keys_ksk, input_cts, threads=8, keys_bskp=None, definitional=False):
     """input_cts [n_inputs][kN+1] uint64 -> output ciphertexts [n_out][kN+1].
-    keys_bskp: pair bootstrapping key -> every bootstrap is the oracle's two-bits-per-step blind rotation"""
+    keys_bskp: pair bootstrapping key -> every bootstrap is the oracle's two-bits-per-step blind rotation.
+    definitional: pair bootstraps by tfhe_oracle.c's orc_pbs_pairs instead of the tuned leg (slow; small programs)"""
     W1 = prm.big_dim + 1
-    fast = orc.Fast(prm, keys_bsk, keys_ksk) if keys_bskp is None else None
+    fast = orc.Fast(prm, keys_bsk, keys_ksk, bskp=keys_bskp) if not definitional else None
     luts = prog.lut_polynomials(prm.N)
     vals = np.zeros((prog.n_slots, W1), np.uint64)
     vals[prog.input_slots] = input_cts

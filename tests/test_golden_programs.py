@@ -132,6 +132,26 @@ def test_encrypted_execution_on_the_oracle_pair_blind_rotation(oracle):
     out = run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp)
     dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
     assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[0])
+    # the tuned pair leg and the definitional one give the same ciphertexts through the whole program
+    assert np.array_equal(out, run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp, definitional=True))
+
+
+def test_whole_inversion_under_encryption_on_the_oracle_default_pipeline(oracle):
+    """the reference's 2x2 inversion as compiled by default (packed products, same-source fusion, borrow chains three
+    digits per level) executed on ENCRYPTED inputs with the pair blind rotation by the CPU oracle: decrypted digits equal
+    the reference's clear path -- the same check tests/test_gpu_circuits.py makes on the B200"""
+    from oracle_exec import run_program_oracle
+    path = os.path.join(HERE, "golden", "inv2_low.npz")
+    z, prog = np.load(path), Program.load(path)
+    assert prog.width == 4 and prog.stats["collapsed_borrows"] > 400
+    prm = PR.TOY_2048_L1
+    keys = oracle.Keys(prm, seed=12)
+    bskp = oracle.keygen_bsk_pairs(prm, 12, keys.s, keys.S)
+    x = z["golden_inputs"].astype(np.int64)[2]
+    cts = np.stack([oracle.encrypt_big(prm, keys.S, 12, i, PR.encode(int(m), prog.width)) for i, m in enumerate(x)])
+    out = run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp, threads=os.cpu_count() or 4)
+    dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
+    assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[2])
 
 
 def test_division_with_collapsed_borrow_chains_under_encryption_on_the_oracle(oracle):

@@ -66,6 +66,22 @@ def test_ciphertexts_equal_oracle_execution_pair_blind_rotation(native, oracle):
     assert not np.array_equal(out.cts, out1.cts)            # same message, different noise
 
 
+def test_whole_inversion_ciphertexts_equal_oracle_execution(native, oracle):
+    """the reference's 2x2 inversion, default pipeline (pair blind rotation): 3,242 bootstraps over 220 levels leave
+    exactly the ciphertexts the CPU oracle computes"""
+    from oracle_exec import run_program_oracle
+    prog, x, want = load("inv2_low")
+    prm = TOY_FOR_WIDTH[prog.width]
+    circuit = fhe.Circuit.from_program(prog, prm)
+    assert circuit.params.bsk_group == 2
+    enc = circuit.encrypt(x[3])
+    out = circuit.run(enc)
+    ref = run_program_oracle(oracle, prog, prm, None, circuit.keys.ksk, enc.cts, keys_bskp=circuit.keys.bskp,
+                             threads=os.cpu_count() or 4)
+    assert np.array_equal(out.cts, ref)
+    assert np.array_equal(circuit.decrypt(out), want[3])
+
+
 def test_secure_parameters_qfloat_add(native):
     """128-bit parameter set chosen by the noise model for this circuit's width and norm"""
     prog, x, want = load("qf_add_medium")

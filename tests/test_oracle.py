@@ -130,3 +130,23 @@ def test_lincomb(oracle, toy):
     cts = np.stack([oracle.encrypt_big(prm, keys.S, 11, i, PR.encode(m, w)) for i, m in enumerate(msgs)])
     out = oracle.lincomb(cts, [0, 1, 2], [2, -1, 3], PR.encode(4, w))
     assert PR.decode_signed(oracle.phase(keys.S, out), w) == 2 * 3 - 5 + 3 * 1 + 4
+
+
+def test_fast_pair_leg_matches_definitional_pair_bootstrap(oracle):
+    """tfhe_oracle_fast.c's pair blind rotation (monomials in the transform domain, as the kernels do it) against
+    tfhe_oracle.c's orc_pbs_pairs (monomials applied to each product in the coefficient domain), incl. two levels"""
+    from bounty_matrix_inversion_b200 import params as PR
+    for prm in (PR.TOY_1024_L1, PR.TOY_2048):
+        keys = oracle.Keys(prm, seed=21)
+        bskp = oracle.keygen_bsk_pairs(prm, 21, keys.s, keys.S)
+        fast = oracle.Fast(prm, None, keys.ksk, bskp=bskp)
+        table = [(3 * m + 2) % 8 for m in range(8)]
+        lut = PR.lut_polynomial([PR.encode(t, 3) for t in table], 3, prm.N)
+        for m in (0, 5, 7):
+            small = oracle.keyswitch(prm, keys.ksk, oracle.encrypt_big(prm, keys.S, 21, m, PR.encode(m, 3)))
+            if m == 7:
+                small[0] = small[1] = small[4] = 0                  # a skipped pair and a half pair
+            want = oracle.pbs_pairs(prm, bskp, lut, small)
+            assert np.array_equal(fast.pbs(lut, small), want)
+            if m != 7:
+                assert PR.decode(oracle.phase(keys.S, want), 3) == table[m]
