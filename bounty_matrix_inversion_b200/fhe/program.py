@@ -289,6 +289,11 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     # True: as many digits per level as the message space holds with the spans taken exactly (three base-2 digits in
     # 4 bits); 2: two digits, and the previous source may leave its span by one where that still fits
     margins = (1, 0) if collapse_borrows == 2 and collapse_borrows is not True else (0,)
+    # "prefix": all borrows of a chain from block signs combined lexicographically, depth ~ 2 log3(digits)
+    prefix_ok = (collapse_borrows == "prefix" and size >= 16 and a_span[0] >= -1 and a_span[1] <= 1
+                 and span_lo >= -2 and span_hi <= 1)
+    chain = {}                 # representative base of a chain borrow -> its leaves [(terms, const)], lowest digit first
+    off16 = (size - 16) // 2 + 8 if size >= 16 else 0
 
     def resolve(src):
         terms = {}
@@ -326,7 +331,60 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         state["nu2"] = max(state["nu2"], sum(c * c for _b, c in key[0]))
         return base
 
+    def _weighted(parts):
+        """sum_j 2^j parts[j] as (terms, const)"""
+        terms, const = {}, 0
+        for j, (t, c) in enumerate(parts):
+            for b, cf in t.items():
+                v = terms.get(b, 0) + (cf << j)
+                if v:
+                    terms[b] = v
+                else:
+                    terms.pop(b, None)
+            const += c << j
+        return terms, const
+
+    def _sign_digit(parts):
+        """a value in {-1, 0, 1} with the lexicographic sign of up to three such digits (least significant first)"""
+        if len(parts) == 1:
+            return parts[0]
+        terms, const = _weighted(parts)
+        rep = add_lookup(None, (tuple(sorted(terms.items())), const + off16), np.sign(dom - off16))
+        return {rep: 1}, 0
+
+    def _segment(leaves, level, idx):
+        """sign digit of the leaves [idx 3^level, (idx + 1) 3^level)"""
+        if level == 0:
+            return leaves[idx]
+        return _sign_digit([_segment(leaves, level - 1, 3 * idx + j) for j in range(3)])
+
+    def _prefix(leaves, level, count):
+        """sign digit of the leaves [0, count 3^level)"""
+        if count <= 3:
+            return _sign_digit([_segment(leaves, level, j) for j in range(count)])
+        q, r = divmod(count, 3)
+        return _sign_digit([_prefix(leaves, level + 1, q)] + [_segment(leaves, level, 3 * q + j) for j in range(r)])
+
+    def _prefix_borrow(jb, terms, scale):
+        for b1, c1 in terms.items():
+            if c1 != -1 or b1 not in chain:
+                continue
+            leaves = chain[b1] + [({b: c for b, c in terms.items() if b != b1}, jb.const)]
+            k, r = divmod(len(leaves), 3)
+            parts = ([_prefix(leaves, 1, k)] if k else []) + [leaves[3 * k + j] for j in range(r)]
+            t_terms, t_const = _weighted(parts)
+            rep = add_lookup(jb.base, (tuple(sorted(t_terms.items())), t_const + off16), scale * (dom - off16 < 0))
+            if rep != jb.base:
+                subst[jb.base] = {rep: 1}
+            if scale == 1:
+                chain.setdefault(rep, leaves)
+            state["collapsed"] += 1
+            return True
+        return False
+
     def _collapse_borrow(jb, terms, scale):
+        if prefix_ok:
+            return _prefix_borrow(jb, terms, scale)
         for b1, c1 in terms.items():
             if c1 != -1 or b1 not in lt0_src:
                 continue
@@ -375,6 +433,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
                 subst[jb.base] = {rep: 1}
             if lt0 == 1:
                 lt0_src.setdefault(rep, (dict(terms), jb.const, min(g.lo, span_lo), max(g.hi, span_hi)))
+                chain.setdefault(rep, [(dict(terms), jb.const)])
             continue
         # one bit too wide: sign through the padding bit, then negacyclic + cyclic halves (module docstring)
         assert bits[int(j)] <= W + 1, "lookup more than one bit wider than the program width"

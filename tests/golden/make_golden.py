@@ -101,10 +101,13 @@ CASES = {
     "inv2_low": lambda: inversion_case(2, "low"),
     "inv2_low_tensorized": lambda: inversion_case(2, "low", tensorize=True),
     "inv2_low_quarter_square": lambda: inversion_case(2, "low"),       # compiled with Concrete's two-lookup product lowering
+    "inv2_low_prefix": lambda: inversion_case(2, "low"),               # borrow chains by parallel prefix (latency-oriented)
     "inv2_medium": lambda: inversion_case(2, "medium"),
     "inv3_low": lambda: inversion_case(3, "low", n_golden=4),
+    "inv3_low_prefix": lambda: inversion_case(3, "low", n_golden=4),
     "inv3_medium": lambda: inversion_case(3, "medium", n_golden=2),
     "inv4_high": lambda: inversion_case(4, "high", n_golden=2),
+    "inv4_high_prefix": lambda: inversion_case(4, "high", n_golden=2),
     "qf_add_medium": lambda: qfloat_op_case("add", "medium"),
     "qf_sub_medium": lambda: qfloat_op_case("sub", "medium"),
     "qf_mul_medium": lambda: qfloat_op_case("mul", "medium"),
@@ -120,7 +123,8 @@ def main():
         fn, inputset, ins, meta = CASES[name]()
         comp = fhe.Compiler(fn, {"x": "encrypted", "y": "encrypted"} if "inv" in name else {"arrays": "encrypted", "signs": "encrypted"})
         circuit = comp.compile(inputset, fhe.Configuration(
-            tfhe_params="deferred", multiplication="quarter_square" if name.endswith("quarter_square") else "auto"))
+            tfhe_params="deferred", multiplication="quarter_square" if name.endswith("quarter_square") else "auto",
+            collapse_borrows="prefix" if name.endswith("_prefix") else True))
         prog = circuit.program
         expected = np.stack([np.asarray(fn(a, s)).astype(np.int64).reshape(-1) for a, s in ins])    # reference clear path
         flat_in = np.stack([np.concatenate([np.asarray(a).reshape(-1), np.asarray(s).reshape(-1)]) for a, s in ins]).astype(np.int64)

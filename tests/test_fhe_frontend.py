@@ -341,6 +341,30 @@ def test_borrow_chain_resolves_several_digits_per_level():
         assert np.array_equal(c.program.evaluate_clear(grid), base)
 
 
+@pytest.mark.parametrize("n", [5, 9, 24, 31])
+def test_borrow_chain_by_parallel_prefix(n):
+    """collapse_borrows="prefix": block signs sign(4 x2 + 2 x1 + x0) compose lexicographically, so every borrow of an
+    n-digit subtraction is out after about 2 log3(n) levels (lookups + a third); same digits as the plain chain"""
+    r = np.random.default_rng(30 + n)
+    inputset = [(r.integers(0, 2, n), r.integers(0, 2, n)) for _ in range(80)]
+    comp = fhe.Compiler(_subtract_digits, {"a": "encrypted", "b": "encrypted"})
+    cfg = lambda **kw: fhe.Configuration(tfhe_params=PR.TOY_1024, slack_bits=2, **kw)
+    plain, chain3, prefix = (comp.compile(inputset, cfg(collapse_borrows=c)) for c in (False, True, "prefix"))
+    depth = {5: 2, 9: 3, 24: 5, 31: 5}[n]
+    assert prefix.statistics["levels"] == depth <= chain3.statistics["levels"] == (n + 2) // 3
+    assert plain.statistics["pbs"] <= prefix.statistics["pbs"] <= 1.5 * plain.statistics["pbs"]
+    x = r.integers(0, 2, (20000, 2 * n))
+    x[0], x[1] = 0, 1                                           # all borrows propagate / none
+    x[2, :n], x[2, n:] = 0, 1                                   # 0 - 11..1: a borrow out of every digit
+    x[3, :n], x[3, n:] = 1, 0
+    x[4] = 0; x[4, 2 * n - 1] = 1                               # 0 - 1: one borrow rippling through every block
+    base = plain.program.evaluate_clear(x)
+    assert np.array_equal(prefix.program.evaluate_clear(x), base)
+    assert np.array_equal(chain3.program.evaluate_clear(x), base)
+    want = np.stack([np.asarray(_subtract_digits(row[:n], row[n:])) for row in x[:200]])
+    assert np.array_equal(base[:200], want)
+
+
 def test_borrow_collapse_leaves_other_threshold_chains_alone():
     """[A + b < 0], [A - 2 b < 0] and [A - f(S) < 0] with f not a sign test are not the borrow pattern"""
     r = np.random.default_rng(22)

@@ -136,6 +136,24 @@ def test_encrypted_execution_on_the_oracle_pair_blind_rotation(oracle):
     assert np.array_equal(out, run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp, definitional=True))
 
 
+def test_prefix_compiled_inversion_under_encryption_on_the_oracle(oracle):
+    """same inversion compiled with collapse_borrows="prefix" (fewer levels, more lookups): encrypted execution on the CPU
+    oracle decrypts to the same reference digits"""
+    from oracle_exec import run_program_oracle
+    path = os.path.join(HERE, "golden", "inv2_low_prefix.npz")
+    z, prog = np.load(path), Program.load(path)
+    base = Program.load(os.path.join(HERE, "golden", "inv2_low.npz"))
+    assert len(prog.levels) < len(base.levels) and base.n_pbs < prog.n_pbs < 1.15 * base.n_pbs
+    prm = PR.TOY_2048_L1
+    keys = oracle.Keys(prm, seed=13)
+    bskp = oracle.keygen_bsk_pairs(prm, 13, keys.s, keys.S)
+    x = z["golden_inputs"].astype(np.int64)[1]
+    cts = np.stack([oracle.encrypt_big(prm, keys.S, 13, i, PR.encode(int(m), prog.width)) for i, m in enumerate(x)])
+    out = run_program_oracle(oracle, prog, prm, None, keys.ksk, cts, keys_bskp=bskp, threads=os.cpu_count() or 4)
+    dec = np.array([PR.decode_signed(oracle.phase(keys.S, c), prog.width) for c in out])
+    assert np.array_equal(dec, z["golden_outputs"].astype(np.int64)[1])
+
+
 def test_whole_inversion_under_encryption_on_the_oracle_default_pipeline(oracle):
     """the reference's 2x2 inversion as compiled by default (packed products, same-source fusion, borrow chains three
     digits per level) executed on ENCRYPTED inputs with the pair blind rotation by the CPU oracle: decrypted digits equal
