@@ -1,5 +1,5 @@
 """Which reference source lines the critical path of a compiled circuit runs through (build container only: traces the
-unmodified reference from /root/reference).  usage: critical_path.py CASE   (a key of tests/golden/make_golden.py CASES)"""
+unmodified reference from /root/reference).  usage: critical_path.py CASE [prefix]   (CASE: a key of tests/golden/make_golden.py CASES)"""
 import collections
 import os
 import sys
@@ -27,7 +27,7 @@ def patched(self, src, f, group, vals):
 tracing.Trace.new_lookup = patched
 enc = {"arrays": "encrypted", "signs": "encrypted"} if name.startswith("qf") else {"x": "encrypted", "y": "encrypted"}
 trace, outs, _shapes, _ = mg.fhe.Compiler(fn, enc).trace(inputset)
-prog = lower(trace, outs, (len(outs),))
+prog = lower(trace, outs, (len(outs),), collapse_borrows="prefix" if "prefix" in sys.argv[2:] else True)
 level_of, job_info = prog.debug["level_of"], prog.debug["job_info"]
 site_of = {}
 for jb in trace.jobs:                      # representative -> site of the first traced lookup it stands for
@@ -44,5 +44,6 @@ while b is not None:
     preds = [t for t, _c in job_info[b][0][0] if t in level_of]
     b = max(preds, key=level_of.get) if preds else None
 print(f"{name}: {prog.n_pbs} lookups, {len(prog.levels)} levels; critical path by reference call site:")
-for site, cnt in collections.Counter(site_of.get(b, "(split helper)") for b in path).most_common(12):
+for site, cnt in collections.Counter(site_of.get(b, "(derived: prefix-scan sign digit)") for b in path).most_common(12):
     print(f"{cnt:6d}  {site}")
+
