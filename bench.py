@@ -10,7 +10,7 @@ batched lincomb -> keyswitch -> PBS launch group.  PBS/s = table lookups execute
   value : inputs (ciphertexts) already resident in HBM, CUDA-event timed
   e2e   : same step through Circuit.run(), i.e. HOST ciphertext buffers in, HOST ciphertext buffers out
   --impl reference : the CPU restatement (oracle/tfhe_oracle_fast.c, all host threads) on a bounded sample
-  --inversion X    : additionally time one encrypted inversion (X = 2|3|4 -> tests/golden/inv{X}_low.npz, or a program
+  --inversion X    : additionally time one encrypted inversion (default on one GPU: inv3_low_prefix; X = 2|3|4 -> tests/golden/inv{X}_low.npz, or a program
                      name such as inv3_medium / inv4_high)
 
 Multi-GPU: launched by torchrun; the pairs are independent, so every rank takes its own `--pairs`
@@ -172,8 +172,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=48, help="QFloat pairs (batch lanes) per step and per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--inversion", default="", help="also time one encrypted inversion: 2 | 3 | 4 (low precision) or a "
-                                                   "compiled program in tests/golden, e.g. inv3_medium, inv4_high")
+    ap.add_argument("--inversion", default="auto", help="also time one encrypted inversion: 2 | 3 | 4 (low precision), a "
+                                                       "compiled program in tests/golden (e.g. inv3_medium, inv4_high_prefix), "
+                                                       "none, or auto = the 3x3 low-precision one on a single GPU")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -302,8 +303,15 @@ def main():
     dev_ms, e2e_ms = times.tolist()
 
     inv = None
-    if args.inversion:
-        inv = time_inversion(args.inversion, fhe, PR, local, rank, world, dist if world > 1 else None)
+    which = args.inversion if args.inversion != "auto" else ("inv3_low_prefix" if world == 1 else "none")
+    if which and which != "none":
+        if world > 1:
+            inv = time_inversion(which, fhe, PR, local, rank, world, dist)
+        else:
+            try:                                   # the second half of the headline metric; never at the price of the line
+                inv = time_inversion(which, fhe, PR, local, rank, world, None)
+            except Exception as e:                 # noqa: BLE001
+                inv = {"program": which, "error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         total = pbs_per_step * world * args.steps
