@@ -25,6 +25,7 @@ Keyswitch rows that legitimately use the padding bit are flagged `Level.full`.
 from __future__ import annotations
 
 import hashlib
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -169,6 +170,14 @@ class Program:
         return (out[0], bad[0]) if single else (out, bad)
 
 
+class _Pseudo:
+    """stand-in for a traced lookup [const + terms < 0] derived from another one"""
+    __slots__ = ("base", "const")
+
+    def __init__(self, base, const):
+        self.base, self.const = base, const
+
+
 _PROBE = np.arange(-70, 71, dtype=np.int64)
 
 
@@ -269,7 +278,8 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     subst = {}                 # traced base -> {representative base: coefficient} where they differ
     job_info = {}              # representative base -> (src key, table id)
     full_keys = set()          # keyswitch rows that use the padding bit on purpose
-    state = {"nu2": 1, "next": n_in + len(jobs), "split": 0, "collapsed": 0}
+    state = {"nu2": 1, "next": n_in + len(jobs), "split": 0, "collapsed": 0, "bitwise_folded": 0}
+    bit_inputs = {b for b, (lo, hi) in enumerate(getattr(trace, "input_ranges", [])[:n_in]) if lo >= 0 and hi <= 1}
     split_of = {}              # helper lookup of a split -> the traced lookup it serves (debug only)
     lt0_src = {}               # representative base of a lookup [S < 0] -> (terms of S, constant of S, observed min, max)
     # A borrow chain is the same digit recurrence at every position, but a given position may have shown only part of
@@ -365,7 +375,7 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         q, r = divmod(count, 3)
         return _sign_digit([_prefix(leaves, level + 1, q)] + [_segment(leaves, level, 3 * q + j) for j in range(r)])
 
-    def _prefix_borrow(jb, terms, scale):
+    def _prefix_borrow(jb, terms, uv):
         for b1, c1 in terms.items():
             if c1 != -1 or b1 not in chain:
                 continue
@@ -373,18 +383,44 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
             k, r = divmod(len(leaves), 3)
             parts = ([_prefix(leaves, 1, k)] if k else []) + [leaves[3 * k + j] for j in range(r)]
             t_terms, t_const = _weighted(parts)
-            rep = add_lookup(jb.base, (tuple(sorted(t_terms.items())), t_const + off16), scale * (dom - off16 < 0))
+            rep = add_lookup(jb.base, (tuple(sorted(t_terms.items())), t_const + off16), np.where(dom - off16 < 0, uv[0], uv[1]))
             if rep != jb.base:
                 subst[jb.base] = {rep: 1}
-            if scale == 1:
+            if uv == (1, 0):
                 chain.setdefault(rep, leaves)
             state["collapsed"] += 1
             return True
         return False
 
-    def _collapse_borrow(jb, terms, scale):
+    def _is_bit(b):
+        if b < n_in:
+            return b in bit_inputs
+        if b - n_in < len(jobs):
+            v = jobs[b - n_in].out_vals
+            return v.size > 0 and v.min() >= 0 and v.max() <= 1
+        return b in chain                                      # derived lookups: only chain borrows are known bits
+
+    def _bitwise_on_borrow(jb, terms):
+        if len(terms) != 2:
+            return None
+        (b0, c0), (b1, c1) = terms.items()
+        for (bb, cb), (ob, co) in (((b0, c0), (b1, c1)), ((b1, c1), (b0, c0))):
+            if bb in chain and cb > 0 and co > 0 and _is_bit(ob):
+                pts = np.array([jb.const, jb.const + co, jb.const + cb, jb.const + cb + co], dtype=np.int64)   # (B, o) = 00 01 10 11
+                try:
+                    tt = tuple(int(v) for v in np.broadcast_to(np.asarray(jb.fn(pts)), (4,)))
+                except Exception:
+                    return None
+                if tt[0] == tt[1] == tt[2] != tt[3]:            # a function of B & o  (digit 1 - o)
+                    return {bb: -1, ob: -1}, 1, (tt[3], tt[0])
+                if tt[1] == tt[2] == tt[3] != tt[0]:            # a function of B | o  (digit -o)
+                    return {bb: -1, ob: -1}, 0, (tt[3], tt[0])
+        return None
+
+    def _collapse_borrow(jb, terms, uv):
+        """uv: the lookup is u where its source is negative, v elsewhere ((1, 0): a borrow bit)"""
         if prefix_ok:
-            return _prefix_borrow(jb, terms, scale)
+            return _prefix_borrow(jb, terms, uv)
         for b1, c1 in terms.items():
             if c1 != -1 or b1 not in lt0_src:
                 continue
@@ -408,11 +444,12 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
             t_const = M * jb.const + s_const
             offset = (size - (t_hi - t_lo + 1)) // 2 - t_lo
             key = (tuple(sorted(t_terms.items())), t_const + offset)
-            rep = add_lookup(jb.base, key, scale * (dom - offset < 0))
+            rep = add_lookup(jb.base, key, np.where(dom - offset < 0, uv[0], uv[1]))
             if rep != jb.base:
                 subst[jb.base] = {rep: 1}
-            if scale == 1:
+            if uv == (1, 0):
                 lt0_src.setdefault(rep, (t_terms, t_const, t_lo, t_hi))
+                chain.setdefault(rep, [(t_terms, t_const)])
             state["collapsed"] += 1
             return True
         return False
@@ -422,8 +459,15 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
         g = jb.group
         terms = resolve(jb.terms)
         lt0 = scales.get(int(j), 0)
-        if lt0 and _collapse_borrow(jb, terms, lt0):
+        if lt0 and _collapse_borrow(jb, terms, (lt0, 0)):
             continue
+        if collapse_borrows and not lt0 and not os.environ.get("BMI_NO_FOLD"):
+            # borrow & bit, borrow | bit (the overflow test after a subtraction, base_p_arrays.py:134/137) are one more,
+            # most significant, digit of the same chain: [1 - o - B < 0] = B & o, [-o - B < 0] = B | o
+            as_digit = _bitwise_on_borrow(jb, terms)
+            if as_digit is not None and _collapse_borrow(_Pseudo(jb.base, as_digit[1]), as_digit[0], as_digit[2]):
+                state["bitwise_folded"] += 1
+                continue
         if (g.hi - g.lo + 1) + 2 * guard <= size or not narrowed:
             offset = (size - (g.hi - g.lo + 1)) // 2 - g.lo           # centre [lo, hi] in [0, 2^W)
             key = (tuple(sorted(terms.items())), jb.const + offset)
@@ -538,6 +582,6 @@ def lower(trace, outputs, out_shape, slack_bits: int = 0, min_width: int = 1, sp
     prog.stats = {"traced_lookups": len(jobs), "live_lookups": int(live.sum()), "pbs": prog.n_pbs, "keyswitches": prog.n_ks,
                   "levels": n_levels, "tables": len(tables), "slots": n_slots, "width": W, "nu2": int(nu2),
                   "max_level_pbs": max((len(l.job_ks) for l in levels), default=0), "split_lookups": state["split"], "top_width_lookups": n_top,
-                  "collapsed_borrows": state["collapsed"]}
+                  "collapsed_borrows": state["collapsed"], "bitwise_folded": state["bitwise_folded"]}
     prog.debug = {"level_of": level_of, "subst": subst, "job_info": job_info, "split_of": split_of}      # for scripts/critical_path.py; not saved
     return prog
