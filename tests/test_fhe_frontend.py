@@ -380,3 +380,36 @@ def test_borrow_collapse_leaves_other_threshold_chains_alone():
     inputset = [(r.integers(0, 3, 4), r.integers(0, 3, 4)) for _ in range(80)]
     c = check(fn, inputset)
     assert c.statistics["collapsed_borrows"] == 0 and c.statistics["levels"] == 2
+
+
+def _subtract_or_keep(a, b, e):
+    """one step of a restoring division: a - b if it does not underflow (and no extra digit e is set), else a"""
+    n = a.size
+    borrow = 0
+    d = a - b
+    diff = fhe.zeros(n)
+    for i in range(n):
+        t = d[-i - 1] - borrow
+        borrow = t < 0
+        diff[-i - 1] = t + 2 * borrow
+    lt = borrow | (np.sum(e) > 0)
+    return diff * (1 - lt) + a * lt
+
+
+@pytest.mark.parametrize("mode", [True, "prefix"])
+def test_overflow_test_joins_the_borrow_chain(mode):
+    n = 9
+    r = np.random.default_rng(3)
+    sample = lambda: (r.integers(0, 2, n), r.integers(0, 2, n), r.integers(0, 2, 2) * r.integers(0, 2, 2))
+    inputset = [sample() for _ in range(200)]
+    comp = fhe.Compiler(_subtract_or_keep, {"a": "encrypted", "b": "encrypted", "e": "encrypted"})
+    cfg = lambda **kw: fhe.Configuration(tfhe_params=PR.TOY_1024, slack_bits=1, **kw)
+    plain = comp.compile(inputset, cfg(collapse_borrows=False))
+    fast = comp.compile(inputset, cfg(collapse_borrows=mode))
+    assert plain.program.width == fast.program.width == 4
+    assert fast.statistics["bitwise_folded"] >= 1 and fast.statistics["levels"] <= 5 < plain.statistics["levels"]
+    x = np.stack([np.concatenate(sample()) for _ in range(5000)])
+    got = fast.program.evaluate_clear(x)
+    assert np.array_equal(got, plain.program.evaluate_clear(x))
+    for row, out in zip(x[:300], got[:300]):
+        assert np.array_equal(out, _subtract_or_keep(row[:n], row[n:2 * n], row[2 * n:]))
