@@ -396,9 +396,9 @@ def _subtract_or_keep(a, b, e):
     return diff * (1 - lt) + a * lt
 
 
-@pytest.mark.parametrize("mode", [True, "prefix"])
-def test_overflow_test_joins_the_borrow_chain(mode):
-    n = 9
+@pytest.mark.parametrize("mode, n", [(True, 8), ("prefix", 9), ("prefix", 8)])
+def test_overflow_test_joins_the_borrow_chain(mode, n):
+    """(a chain of three digits per level has room for the extra digit only where its last group is not full)"""
     r = np.random.default_rng(3)
     sample = lambda: (r.integers(0, 2, n), r.integers(0, 2, n), r.integers(0, 2, 2) * r.integers(0, 2, 2))
     inputset = [sample() for _ in range(200)]
