@@ -9,207 +9,21 @@
 #include <utility>
 #include <vector>
 
-#include "../../include/bmi_tfhe.h"
-#include "host_common.h"
-#include "split.cuh"
+#include "launchers.cuh"
+#include "leveled.cuh"
 
 namespace bmi_host {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 }  // namespace bmi_host
-using bmi_host::set_error;
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
-            return BMI_ECUDA;                                                                      \
-        }                                                                                          \
-    } while (0)
-
-struct bmi_ctx {
-    bmi_params p;
-    int device, logN;
-    u64 ninv;
-    u64 *d_tw = nullptr, *d_twi = nullptr, *d_ksk = nullptr, *d_luts = nullptr;
-    u64* d_bsk[3] = {nullptr, nullptr, nullptr};   // transform-domain key: throughput build / latency build / 8-CTA split kernel
-    // pair blind rotation (bmi_ctx_load_bsk_pairs): the pair key in the same three layouts, per layout the exponent of
-    // every transform slot's evaluation point, and the powers of psi
-    u64* d_bskp[3] = {nullptr, nullptr, nullptr};
-    u32* d_expo[3] = {nullptr, nullptr, nullptr};
-    u64* d_pw = nullptr;
-    bool pairs = false;
-    int n_luts = 0;
-    int num_sms = 148;
-    int64_t launches = 0;
-    int split_clusters = -1;   // resident 8-CTA clusters of the split kernel (queried once)
-    bool split_async = true;  // split kernel synchronised by mbarriers + st.async (BMI_SPLIT_ASYNC=0: cluster barriers)
-    bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
-    int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel
-    // scratch for the host-buffer convenience path
-    u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
-    int *w_idx = nullptr, *w_lut = nullptr;
-    int64_t w_cap = 0;
-    u64* ks_partial = nullptr;   // per-slice keyswitch sums (small batches)
-    u64* d_ks_corr = nullptr;    // [n+1] B/2 * column sums of the keyswitch key (digits are used shifted by B/2)
-    size_t ks_partial_cap = 0;
-};
+#define BMI_EXTERN_L(L)                                                                                  \
+    extern template int setup_attrs<L>(const bmi_ctx*);                                                  \
+    extern template int launch_convert<L>(bmi_ctx*, const u64*, u64* const*, int64_t, int64_t, cudaStream_t); \
+    extern template int launch_pbs<L>(bmi_ctx*, PbsArgs, cudaStream_t);                                  \
+    extern template int launch_polymul<L>(bmi_ctx*, const u64*, const u64*, u64*, int, cudaStream_t);
+BMI_EXTERN_L(10) BMI_EXTERN_L(11) BMI_EXTERN_L(12) BMI_EXTERN_L(13) BMI_EXTERN_L(14)
 
 namespace {
-
-constexpr int kMaxSmem = 227 * 1024;   // dynamic shared memory a CTA can opt into on sm_100
-
-size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
-
-size_t split_smem(const bmi_ctx* c) { return (size_t)6 * (c->p.N / 4) * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
-size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
-
-template <int L>
-constexpr int split_convert_e() { return L <= 12 ? 2 : L == 13 ? 3 : 4; }
-constexpr int kMaxClusterL = 13;   // largest polynomial the 2-CTA cluster kernels hold in shared memory; above: split kernel only
-
-template <int L>
-int setup_attrs(const bmi_ctx* c) {
-    CK(cudaFuncSetAttribute(pbs_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_split_async_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_split_async_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
-    CK(cudaFuncSetAttribute(polymul_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SplitCfg<L>::M * 8));
-    CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, split_convert_e<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    if constexpr (L <= kMaxClusterL) {
-        constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
-        const int sm = (int)pbs_smem(c), sms = (int)pbs_smem_staged(c);
-        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
-        if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
-        CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-        CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-        CK(cudaFuncSetAttribute(polymul_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-        CK(cudaFuncSetAttribute(polymul_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
-    }
-    return BMI_OK;
-}
-
-// both layouts of the transform-domain key: [0] throughput build (E = 4), [1] latency build
-template <int L>
-int launch_convert(bmi_ctx* c, const u64* src, u64* const* dst, int64_t p0, int64_t polys, cudaStream_t st) {
-    const size_t off = (size_t)p0 * c->p.N;
-    if constexpr (L <= kMaxClusterL) {
-        constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
-        bsk_convert_kernel<L, ET><<<(unsigned)polys, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(src, dst[0] + off, c->d_tw, c->ninv);
-        bsk_convert_kernel<L, EL><<<(unsigned)polys, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(src, dst[1] + off, c->d_tw, c->ninv);
-        c->launches += 2;
-    }
-    if (c->p.bsk_l == 1) {
-        constexpr int EC = split_convert_e<L>();
-        bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, dst[2] + off, c->d_tw, c->ninv);
-        c->launches++;
-    }
-    CK(cudaGetLastError());
-    return BMI_OK;
-}
-
-// how many 8-CTA clusters of the split kernel the GPU keeps resident at once (cluster placement is per GPC)
-template <int L>
-int64_t split_capacity(bmi_ctx* c) {
-    if (c->split_clusters < 0) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(8 * 64);
-        cfg.blockDim = dim3(SplitCfg<L>::T);
-        cfg.dynamicSmemBytes = split_smem(c);
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 8; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, pbs_split_kernel<L>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = c->num_sms / 10; }
-        c->split_clusters = n;
-    }
-    return c->split_clusters;
-}
-
-template <int L>
-int launch_split(bmi_ctx* c, PbsArgs a, int64_t total, cudaStream_t st) {
-    if (c->pairs) {
-        a.bsk_hat = c->d_bskp[2]; a.expo = c->d_expo[2]; a.pw = c->d_pw;
-        pbs_split_async_kernel<L, true><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
-        c->launches++;
-        CK(cudaGetLastError());
-        return BMI_OK;
-    }
-    a.bsk_hat = c->d_bsk[2];
-    if (c->split_async) pbs_split_async_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
-    else pbs_split_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
-    c->launches++;
-    CK(cudaGetLastError());
-    return BMI_OK;
-}
-
-template <int L>
-int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
-    const int64_t total = (int64_t)a.njobs * a.batch;
-    const bool one = a.l == 1;
-    if constexpr (L > kMaxClusterL) {
-        return launch_split<L>(c, a, total, st);
-    } else {
-    constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
-    const unsigned grid = 2 * (unsigned)std::min<int64_t>(total, 1 << 20);      // one CTA pair per ciphertext
-    // While the launch fits the CTA pairs the latency build keeps resident, latency wins; beyond one wave the
-    // 16-coefficients-per-thread build (fewer shared-memory round trips, more ciphertexts per SM) does.
-    int resident = 1;
-    if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true, false>, NttCfg<L, EL>::T, pbs_smem(c));
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
-    const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
-    // A handful of ciphertexts: spread each over an 8-CTA cluster (4 CTAs per polynomial), lowest latency.
-    if (one && (c->pbs_mode == 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) return launch_split<L>(c, a, total, st);
-    const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
-    a.bsk_hat = c->d_bsk[latency ? 1 : 0];
-    const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
-    if (c->pairs) {
-        a.bsk_hat = c->d_bskp[latency ? 1 : 0]; a.expo = c->d_expo[latency ? 1 : 0]; a.pw = c->d_pw;
-        if (latency) pbs_cluster_kernel<L, EL, 1, true, false, true><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
-        else pbs_cluster_kernel<L, ET, TP, true, false, true><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
-        c->launches++;
-        CK(cudaGetLastError());
-        return BMI_OK;
-    }
-    // GGSW rows staged by TMA whenever the extra 2N words still leave room for the CTAs per SM the build is sized for
-    const bool stage = one && c->tma_stage && (latency ? (int)sms <= kMaxSmem : (int)sms * TP <= kMaxSmem);
-    if (latency && stage) pbs_cluster_kernel<L, EL, 1, true, true><<<grid, NttCfg<L, EL>::T, sms, st>>>(a);
-    else if (latency && one) pbs_cluster_kernel<L, EL, 1, true, false><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
-    else if (latency) pbs_cluster_kernel<L, EL, 1, false, false><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
-    else if (stage) pbs_cluster_kernel<L, ET, TP, true, true><<<grid, NttCfg<L, ET>::T, sms, st>>>(a);
-    else if (one) pbs_cluster_kernel<L, ET, TP, true, false><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
-    else pbs_cluster_kernel<L, ET, TP, false, false><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
-    c->launches++;
-    CK(cudaGetLastError());
-    return BMI_OK;
-    }
-}
-
-template <int L>
-int launch_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* out, int count, cudaStream_t st) {
-    if (c->pbs_mode == 3 || L > kMaxClusterL) {
-        polymul_split_kernel<L><<<4 * count, SplitCfg<L>::T, 3 * SplitCfg<L>::M * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
-        c->launches++;
-        CK(cudaGetLastError());
-        return BMI_OK;
-    }
-    if constexpr (L <= kMaxClusterL) {
-        constexpr int EL = latency_e<L>(), ET = throughput_e<L>();
-        if (c->pbs_mode == 1) polymul_kernel<L, EL><<<count, NttCfg<L, EL>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
-        else polymul_kernel<L, ET><<<count, NttCfg<L, ET>::T, (1 << L) * 8, st>>>(a, b, out, c->d_tw, c->d_twi, c->ninv);
-        c->launches++;
-        CK(cudaGetLastError());
-    }
-    return BMI_OK;
-}
 
 #define DISPATCH_L(c, expr)                                  \
     switch ((c)->logN) {                                     \

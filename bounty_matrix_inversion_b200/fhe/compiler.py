@@ -16,7 +16,8 @@ from .program import Program, lower
 
 class Configuration:
     """accepts Concrete's keyword options; the ones this engine understands:
-    tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, seed, device,
+    tfhe_params (explicit TfheParams), p_error_sigmas, slack_bits, device,
+    seed (None = OS entropy, like Concrete's keygen(); an integer = fixed keys for tests and benchmarks only),
     multiplication ("auto" | "quarter_square", see tracing.Trace),
     split_wide ("auto" | True | False), split_guard and collapse_borrows (see program.lower),
     blind_rotation ("pairs" | "single"): two key bits per bootstrap step with the pair key (default wherever the
@@ -27,7 +28,7 @@ class Configuration:
         self.tfhe_params = options.get("tfhe_params")
         self.p_error_sigmas = options.get("p_error_sigmas", 6.5)
         self.slack_bits = options.get("slack_bits", 0)
-        self.seed = options.get("seed", 0x5EED)
+        self.seed = options.get("seed")          # None: keys and encryptions from OS entropy; int: fixed test seed
         self.device = options.get("device", 0)
         self.multiplication = options.get("multiplication", "auto")
         self.split_wide = options.get("split_wide", "auto")
@@ -126,7 +127,6 @@ class Circuit:
         self.in_shapes, self.out_shapes = [tuple(s) for s in in_shapes], [tuple(s) for s in out_shapes]
         self.keys = None
         self._executor = None
-        self._ct_counter = 0
 
     @classmethod
     def from_program(cls, program: Program, params=None, in_shapes=None, out_shapes=None, configuration=None):
@@ -165,8 +165,7 @@ class Circuit:
         self.keygen()
         msg = self._flatten_args(args)
         W = self.program.width
-        cts = self.keys.encrypt([PR.encode(int(m), W) for m in msg], ct_index0=self._ct_counter)
-        self._ct_counter += len(msg)
+        cts = self.keys.encrypt([PR.encode(int(m), W) for m in msg])
         return EncryptedData(cts, batch=False)
 
     def encrypt_batch(self, list_of_args):
@@ -174,8 +173,7 @@ class Circuit:
         self.keygen()
         W = self.program.width
         msgs = np.stack([self._flatten_args(a) for a in list_of_args])
-        cts = self.keys.encrypt([PR.encode(int(m), W) for m in msgs.reshape(-1)], ct_index0=self._ct_counter)
-        self._ct_counter += msgs.size
+        cts = self.keys.encrypt([PR.encode(int(m), W) for m in msgs.reshape(-1)])
         return EncryptedData(cts.reshape(msgs.shape[0], msgs.shape[1], -1), batch=True)
 
     def decrypt(self, result: EncryptedData):

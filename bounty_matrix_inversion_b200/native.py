@@ -34,12 +34,14 @@ _lib = None
 _SIGNATURES = {
     "bmi_version": (C.c_char_p, []),
     "bmi_last_error": (C.c_char_p, []),
-    "bmi_keygen_lwe": (C.c_int, [C.c_void_p, C.c_uint64, U64P]),
-    "bmi_keygen_glwe": (C.c_int, [C.c_void_p, C.c_uint64, U64P]),
-    "bmi_keygen_bsk": (C.c_int, [C.c_void_p, C.c_uint64, U64P, U64P, U64P, C.c_int]),
-    "bmi_keygen_bsk_pairs": (C.c_int, [C.c_void_p, C.c_uint64, U64P, U64P, U64P, C.c_int]),
-    "bmi_keygen_ksk": (C.c_int, [C.c_void_p, C.c_uint64, U64P, U64P, U64P, C.c_int]),
-    "bmi_lwe_encrypt": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, U64P, U64P, C.c_int64, U64P]),
+    "bmi_random_seed": (C.c_int, [C.c_char_p]),
+    "bmi_rng_words": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, U64P, C.c_int64]),
+    "bmi_keygen_lwe": (C.c_int, [C.c_void_p, C.c_char_p, U64P]),
+    "bmi_keygen_glwe": (C.c_int, [C.c_void_p, C.c_char_p, U64P]),
+    "bmi_keygen_bsk": (C.c_int, [C.c_void_p, C.c_char_p, U64P, U64P, U64P, C.c_int]),
+    "bmi_keygen_bsk_pairs": (C.c_int, [C.c_void_p, C.c_char_p, U64P, U64P, U64P, C.c_int]),
+    "bmi_keygen_ksk": (C.c_int, [C.c_void_p, C.c_char_p, U64P, U64P, U64P, C.c_int]),
+    "bmi_lwe_encrypt": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, U64P, U64P, C.c_int64, U64P]),
     "bmi_lwe_phase": (C.c_int, [U64P, C.c_int32, U64P, C.c_int64, U64P]),
     "bmi_ctx_create": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "bmi_ctx_destroy": (C.c_int, [C.c_void_p]),
@@ -91,39 +93,75 @@ def _u64(a):
 
 
 # ------------------------------------------------------------------ client
+def random_seed() -> bytes:
+    """32 bytes of OS entropy (getrandom) through the C ABI"""
+    buf = C.create_string_buffer(32)
+    _check(lib().bmi_random_seed(buf))
+    return buf.raw
+
+
+def rng_words(seed: bytes, stream: int, ctr0: int, count: int) -> np.ndarray:
+    """raw ChaCha20 keystream words of the client generator (known-answer tests)"""
+    out = np.zeros(count, np.uint64)
+    _check(lib().bmi_rng_words(bytes(seed), stream, ctr0, _p(out), count))
+    return out
+
+
+def _test_seeds(seed: int):
+    """three fixed 32-byte seeds from an integer: reproducible keys for tests and benchmarks ONLY"""
+    import hashlib
+    return [hashlib.sha256(b"bmi-fixed-seed/%s/%d" % (tag, int(seed))).digest() for tag in (b"secret", b"evaluation", b"encrypt")]
+
+
 class ClientKeys:
     """secret and evaluation keys of one circuit (host memory)"""
 
-    def __init__(self, params: TfheParams, seed: int, threads: int = 0, evaluation_keys: bool = True,
+    def __init__(self, params: TfheParams, seed=None, threads: int = 0, evaluation_keys: bool = True,
                  pairs: bool = False):
-        """pairs: generate the pair bootstrapping key (two key bits per blind-rotation step, `bskp`) instead of the
+        """seed: None (default) = every key and every encryption draws from OS entropy, the secret keys from a seed of
+        their own; an integer = fixed, publicly derivable seeds for reproducible tests and benchmarks, never for
+        real data.
+        pairs: generate the pair bootstrapping key (two key bits per blind-rotation step, `bskp`) instead of the
         one-GGSW-per-bit key (`bsk`)"""
-        self.params, self.seed = params, int(seed)
+        self.params = params
+        self.deterministic = seed is not None
+        if seed is None:
+            self._sk_seed, self._ev_seed, self._enc_seed = random_seed(), random_seed(), random_seed()
+        else:
+            self._sk_seed, self._ev_seed, self._enc_seed = _test_seeds(seed)
+        self._enc_counter = 0            # ciphertexts encrypted so far under _enc_seed: a counter value is never reused
         bp = BmiParams.of(params)
         L = lib()
         threads = threads or (os.cpu_count() or 1)
         self.s = np.zeros(params.n, np.uint64)
         self.S = np.zeros(params.big_dim, np.uint64)
-        _check(L.bmi_keygen_lwe(C.byref(bp), self.seed, _p(self.s)))
-        _check(L.bmi_keygen_glwe(C.byref(bp), self.seed, _p(self.S)))
+        _check(L.bmi_keygen_lwe(C.byref(bp), self._sk_seed, _p(self.s)))
+        _check(L.bmi_keygen_glwe(C.byref(bp), self._sk_seed, _p(self.S)))
         self.bsk = self.bskp = self.ksk = None
         if evaluation_keys:
             rows = (params.k + 1) * params.bsk_l
             self.ksk = np.zeros((params.big_dim, params.ksk_l, params.n + 1), np.uint64)
             if pairs:
                 self.bskp = np.zeros((params.n // 2, 3, rows, params.k + 1, params.N), np.uint64)
-                _check(L.bmi_keygen_bsk_pairs(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.bskp), threads))
+                _check(L.bmi_keygen_bsk_pairs(C.byref(bp), self._ev_seed, _p(self.s), _p(self.S), _p(self.bskp), threads))
             else:
                 self.bsk = np.zeros((params.n, rows, params.k + 1, params.N), np.uint64)
-                _check(L.bmi_keygen_bsk(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.bsk), threads))
-            _check(L.bmi_keygen_ksk(C.byref(bp), self.seed, _p(self.s), _p(self.S), _p(self.ksk), threads))
+                _check(L.bmi_keygen_bsk(C.byref(bp), self._ev_seed, _p(self.s), _p(self.S), _p(self.bsk), threads))
+            _check(L.bmi_keygen_ksk(C.byref(bp), self._ev_seed, _p(self.s), _p(self.S), _p(self.ksk), threads))
 
-    def encrypt(self, plaintexts, ct_index0: int = 0) -> np.ndarray:
-        """big-key LWE encryptions of field-element plaintexts -> [count][kN+1]"""
+    def encrypt(self, plaintexts, ct_index0=None) -> np.ndarray:
+        """big-key LWE encryptions of field-element plaintexts -> [count][kN+1].  Mask and noise come from the next
+        unused positions of this key set's encryption keystream; `ct_index0` pins the position instead and is accepted
+        only with fixed test seeds (reusing a position under one seed reveals the difference of the two messages)."""
         pt = np.atleast_1d(np.array(plaintexts, dtype=np.uint64))
+        if ct_index0 is None:
+            ct_index0 = self._enc_counter
+            self._enc_counter += pt.size
+        elif not self.deterministic:
+            raise ValueError("ct_index0 is a test hook: it needs ClientKeys(seed=<int>)")
         out = np.zeros((pt.size, self.params.big_dim + 1), np.uint64)
         bp = BmiParams.of(self.params)
-        _check(lib().bmi_lwe_encrypt(C.byref(bp), self.seed, int(ct_index0), _p(self.S), _p(pt), pt.size, _p(out)))
+        _check(lib().bmi_lwe_encrypt(C.byref(bp), self._enc_seed, int(ct_index0), _p(self.S), _p(pt), pt.size, _p(out)))
         return out
 
     def phase(self, cts, small: bool = False) -> np.ndarray:

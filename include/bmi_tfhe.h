@@ -48,18 +48,26 @@ typedef struct bmi_ctx bmi_ctx;
 const char* bmi_version(void);
 const char* bmi_last_error(void);
 
-/* ---- client side (host only, no GPU needed): keys, encryption, decryption ---- */
-int bmi_keygen_lwe(const bmi_params* p, uint64_t seed, uint64_t* h_s /* [n] */);
-int bmi_keygen_glwe(const bmi_params* p, uint64_t seed, uint64_t* h_S /* [k*N] */);
+/* ---- client side (host only, no GPU needed): keys, encryption, decryption ----
+ * All randomness is ChaCha20 keystream under a 32-byte seed.  Production callers fill every seed with
+ * bmi_random_seed (OS entropy) and use DIFFERENT seeds for the secret keys (bmi_keygen_lwe / _glwe), for the
+ * evaluation keys (bmi_keygen_bsk* / _ksk) and for encryption; fixed seeds are for tests and benchmarks only.
+ * Concrete's circuit.keygen() takes no seed either (main.py:177). */
+int bmi_random_seed(uint8_t* seed /* [32] */);
+/* raw generator output, words ctr0 .. ctr0+count-1 of keystream `stream` (self-test entry: known-answer vectors) */
+int bmi_rng_words(const uint8_t* seed, uint64_t stream, uint64_t ctr0, uint64_t* h_out, int64_t count);
+int bmi_keygen_lwe(const bmi_params* p, const uint8_t* seed, uint64_t* h_s /* [n] */);
+int bmi_keygen_glwe(const bmi_params* p, const uint8_t* seed, uint64_t* h_S /* [k*N] */);
 /* bsk[i][r][comp][t]: i<n, r = c*l+(j-1) < (k+1)*l, comp<=k (k = body), coefficient domain */
-int bmi_keygen_bsk(const bmi_params* p, uint64_t seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_bsk, int threads);
+int bmi_keygen_bsk(const bmi_params* p, const uint8_t* seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_bsk, int threads);
 /* pair key for blind rotation two key bits per step (n even): bskp[q][x][r][comp][t], q<n/2,
  * x = 0: GGSW(s_2q s_2q+1), 1: GGSW(s_2q (1 - s_2q+1)), 2: GGSW((1 - s_2q) s_2q+1); 1.5x the size of bsk */
-int bmi_keygen_bsk_pairs(const bmi_params* p, uint64_t seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_bskp, int threads);
+int bmi_keygen_bsk_pairs(const bmi_params* p, const uint8_t* seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_bskp, int threads);
 /* ksk[i][j-1][0..n]: i<k*N, body last */
-int bmi_keygen_ksk(const bmi_params* p, uint64_t seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_ksk, int threads);
-/* `count` big-key encryptions of the plaintexts h_pt (field elements); ciphertext q uses counter ct_index0+q */
-int bmi_lwe_encrypt(const bmi_params* p, uint64_t seed, uint64_t ct_index0, const uint64_t* h_S,
+int bmi_keygen_ksk(const bmi_params* p, const uint8_t* seed, const uint64_t* h_s, const uint64_t* h_S, uint64_t* h_ksk, int threads);
+/* `count` big-key encryptions of the plaintexts h_pt (field elements); ciphertext q uses counter ct_index0+q of the
+ * seed's mask and noise keystreams: a (seed, counter) pair must never be used for two ciphertexts */
+int bmi_lwe_encrypt(const bmi_params* p, const uint8_t* seed, uint64_t ct_index0, const uint64_t* h_S,
                     const uint64_t* h_pt, int64_t count, uint64_t* h_ct /* [count][k*N+1] */);
 /* phases b - <a, key> of `count` ciphertexts of dimension dim */
 int bmi_lwe_phase(const uint64_t* h_key, int32_t dim, const uint64_t* h_ct, int64_t count, uint64_t* h_phase);

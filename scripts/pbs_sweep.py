@@ -22,11 +22,12 @@ def main():
     for name in names:
         prm = SETS[name]
         t0 = time.time()
-        keys = native.ClientKeys(prm, seed=5)
+        pairs = os.environ.get("SWEEP_PAIRS", "0") == "1"
+        keys = native.ClientKeys(prm, seed=5, pairs=pairs)
         t_keys = time.time() - t0
         eng = native.Engine(prm, 0)
         t0 = time.time()
-        eng.load_keys(keys.bsk, keys.ksk)
+        eng.load_keys(keys.bsk, keys.ksk, bskp=keys.bskp)
         t_load = time.time() - t0
         w = 3
         luts = np.stack([PR.lut_polynomial([PR.encode(t, w) for t in range(8)], w, prm.N)])
@@ -43,7 +44,7 @@ def main():
             idx = torch.arange(count, dtype=torch.int32, device="cuda")
             lut = torch.zeros(count, dtype=torch.int32, device="cuda")
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            for it in range(2):
+            for it in range(3):
                 ev[0].record()
                 eng.keyswitch(big, small, count)
                 ev[1].record()
@@ -52,7 +53,7 @@ def main():
                 torch.cuda.synchronize()
             ks_ms, pbs_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
             dec = [PR.decode(int(p), w) for p in keys.phase(out[:4].cpu().numpy().view(np.uint64))]
-            print(json.dumps({"set": prm.name, "mode": mode, "count": count, "ks_ms": round(ks_ms, 3), "pbs_ms": round(pbs_ms, 3),
+            print(json.dumps({"set": prm.name, "pairs": pairs, "mode": mode, "count": count, "ks_ms": round(ks_ms, 3), "pbs_ms": round(pbs_ms, 3),
                               "pbs_per_s": round(count / (pbs_ms + ks_ms) * 1e3, 1), "dec": dec,
                               "keygen_s": round(t_keys, 2), "load_s": round(t_load, 2)}), flush=True)
         eng.close()
