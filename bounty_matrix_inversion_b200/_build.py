@@ -12,7 +12,7 @@ LIB = os.environ.get("BMI_TFHE_LIB") or os.path.join(CSRC, "libbmi_tfhe.so")   #
 OBJ = os.path.join(CSRC, "build")
 SIZES = (10, 11, 12, 13, 14)
 SOURCES = ["engine.cu", "client.cpp", "launch_inst.cu"]
-HEADERS = ["field.cuh", "ntt.cuh", "kernels.cuh", "split.cuh", "leveled.cuh", "launchers.cuh", "host_common.h", "../../include/bmi_tfhe.h"]
+HEADERS = ["field.cuh", "ntt.cuh", "kernels.cuh", "split.cuh", "split2.cuh", "leveled.cuh", "launchers.cuh", "host_common.h", "../../include/bmi_tfhe.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

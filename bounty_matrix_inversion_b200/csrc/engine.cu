@@ -25,6 +25,21 @@ BMI_EXTERN_L(10) BMI_EXTERN_L(11) BMI_EXTERN_L(12) BMI_EXTERN_L(13) BMI_EXTERN_L
 
 namespace {
 
+// Every ABI entry point that launches or allocates runs with the context's device current and restores the caller's.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) { ok = false; set_error("cudaSetDevice failed"); }
+        if (prev == device) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(c)                    \
+    DeviceGuard guard_((c)->device); \
+    if (!guard_.ok) return BMI_ECUDA
+
 #define DISPATCH_L(c, expr)                                  \
     switch ((c)->logN) {                                     \
         case 10: { constexpr int L = 10; return expr; }      \
@@ -42,10 +57,11 @@ int do_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* o, int n, cudaStream
 
 // upload a standard-domain key of `polys` polynomials in slices through a bounded staging buffer, converting slice by
 // slice into every transform-domain layout this parameter set can run (dst[0..2])
-int upload_converted(bmi_ctx* c, const u64* h_key, int64_t polys, u64** dst) {
+int upload_converted(bmi_ctx* c, const u64* h_key, int64_t polys, u64** dst, int layouts) {
     const size_t bytes = (size_t)polys * c->p.N * 8;
-    for (int v = 0; v < 3; v++) {
-        const bool needed = v == 2 ? c->p.bsk_l == 1 : c->logN <= kMaxClusterL;
+    for (int v = 0; v < layouts; v++) {
+        // layout 3 (two-points-per-thread kernel) only when that kernel was selected before the key is loaded
+        const bool needed = v == 3 ? (c->logN <= kMaxSplit2L && c->pbs_mode == 5) : v == 2 ? c->p.bsk_l == 1 : c->logN <= kMaxClusterL;
         if (needed && !dst[v]) CK(cudaMalloc(&dst[v], bytes));
     }
     const int64_t slice = std::min<int64_t>(polys, 4096);
@@ -65,6 +81,8 @@ int upload_converted(bmi_ctx* c, const u64* h_key, int64_t polys, u64** dst) {
 int ensure_scratch(bmi_ctx* c, int64_t count) {
     if (count <= c->w_cap) return BMI_OK;
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
+    c->w_in = c->w_small = c->w_out = nullptr;      // a failed allocation below must not leave dangling pointers behind
+    c->w_idx = c->w_lut = nullptr;
     c->w_cap = 0;
     const size_t big = (size_t)c->p.k * c->p.N + 1;
     CK(cudaMalloc(&c->w_in, count * big * 8));
@@ -77,6 +95,16 @@ int ensure_scratch(bmi_ctx* c, int64_t count) {
     CK(cudaMemcpy(c->w_idx, iota.data(), count * sizeof(int), cudaMemcpyHostToDevice));
     c->w_cap = count;
     return BMI_OK;
+}
+
+int ctx_init_device(bmi_ctx* c) {
+    std::vector<u64> tw, twi;
+    bmi_host::twiddles(c->p.N, tw, twi);
+    CK(cudaMalloc(&c->d_tw, c->p.N * 8));
+    CK(cudaMalloc(&c->d_twi, c->p.N * 8));
+    CK(cudaMemcpy(c->d_tw, tw.data(), c->p.N * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_twi, twi.data(), c->p.N * 8, cudaMemcpyHostToDevice));
+    return do_setup(c);
 }
 
 }  // namespace
@@ -102,32 +130,27 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("no such CUDA device"); return BMI_ECUDA; }
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (!guard.ok) return BMI_ECUDA;
     bmi_ctx* c = new bmi_ctx();
     c->p = *p; c->device = device; c->logN = logN;
     c->ninv = fpow((u64)p->N, BMI_P - 2);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
-    std::vector<u64> tw, twi;
-    bmi_host::twiddles(p->N, tw, twi);
-    CK(cudaMalloc(&c->d_tw, p->N * 8));
-    CK(cudaMalloc(&c->d_twi, p->N * 8));
-    CK(cudaMemcpy(c->d_tw, tw.data(), p->N * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_twi, twi.data(), p->N * 8, cudaMemcpyHostToDevice));
     if (const char* v = getenv("BMI_TMA_STAGE")) c->tma_stage = v[0] == '1';
     if (const char* v = getenv("BMI_SPLIT_ASYNC")) c->split_async = v[0] != '0';
-    int rc = do_setup(c);
-    if (rc) { delete c; return rc; }
+    int rc = ctx_init_device(c);
+    if (rc) { bmi_ctx_destroy(c); return rc; }      // nothing allocated so far outlives a failed create
     *out = c;
     return BMI_OK;
 }
 
 int bmi_ctx_destroy(bmi_ctx* c) {
     if (!c) return BMI_OK;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaFree(c->d_tw); cudaFree(c->d_twi); cudaFree(c->d_bsk[0]); cudaFree(c->d_bsk[1]); cudaFree(c->d_bsk[2]); cudaFree(c->d_ksk); cudaFree(c->d_luts);
     cudaFree(c->w_in); cudaFree(c->w_small); cudaFree(c->w_out); cudaFree(c->w_idx); cudaFree(c->w_lut);
     cudaFree(c->ks_partial); cudaFree(c->d_ks_corr);
-    for (int v = 0; v < 3; v++) { cudaFree(c->d_bskp[v]); cudaFree(c->d_expo[v]); }
+    for (int v = 0; v < 4; v++) { cudaFree(c->d_bskp[v]); cudaFree(c->d_expo[v]); }
     cudaFree(c->d_pw);
     delete c;
     return BMI_OK;
@@ -135,16 +158,27 @@ int bmi_ctx_destroy(bmi_ctx* c) {
 
 int bmi_ctx_load_bsk(bmi_ctx* c, const uint64_t* h_bsk) {
     if (!c || !h_bsk) { set_error("null argument"); return BMI_EINVAL; }
-    CK(cudaSetDevice(c->device));
-    return upload_converted(c, h_bsk, (int64_t)c->p.n * 2 * c->p.bsk_l * 2, c->d_bsk);
+    GUARD(c);
+    u64* dst[4] = {c->d_bsk[0], c->d_bsk[1], c->d_bsk[2], nullptr};
+    const int rc = upload_converted(c, h_bsk, (int64_t)c->p.n * 2 * c->p.bsk_l * 2, dst, 3);
+    for (int v = 0; v < 3; v++) c->d_bsk[v] = dst[v];
+    return rc;
 }
 
 int bmi_ctx_load_bsk_pairs(bmi_ctx* c, const uint64_t* h_bskp) {
     if (!c || !h_bskp) { set_error("null argument"); return BMI_EINVAL; }
     if (c->p.bsk_l != 1 || c->p.n % 2) { set_error("pair blind rotation needs one decomposition level and an even LWE dimension"); return BMI_EINVAL; }
-    CK(cudaSetDevice(c->device));
-    int rc = upload_converted(c, h_bskp, (int64_t)(c->p.n / 2) * 3 * 2 * 2, c->d_bskp);
+    GUARD(c);
+    int rc = upload_converted(c, h_bskp, (int64_t)(c->p.n / 2) * 3 * 2 * 2, c->d_bskp, 4);
     if (rc) return rc;
+    for (int v = 0; v < 4; v++) {   // every layout: K10 <- K11 + K10, K01 <- K11 + K01 (what the pointwise stage multiplies with)
+        if (!c->d_bskp[v]) continue;
+        const size_t third = (size_t)4 * c->p.N, pairs = (size_t)c->p.n / 2;
+        pair_key_sums_kernel<<<(unsigned)((third * pairs + 255) / 256), 256>>>(c->d_bskp[v], third, pairs);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaDeviceSynchronize());
     // powers of psi, and for every layout the exponent of each transform slot's evaluation point: the transform of
     // the monomial X holds the evaluation points themselves (times 1/N, which the conversion folds in)
     const int N = c->p.N;
@@ -159,15 +193,15 @@ int bmi_ctx_load_bsk_pairs(bmi_ctx* c, const uint64_t* h_bskp) {
     std::sort(index.begin(), index.end());
     std::vector<u64> mono(N, 0);
     mono[1] = 1;
-    u64 *d_src = nullptr, *d_dst[3] = {nullptr, nullptr, nullptr};
+    u64 *d_src = nullptr, *d_dst[4] = {nullptr, nullptr, nullptr, nullptr};
     CK(cudaMalloc(&d_src, (size_t)N * 8));
     CK(cudaMemcpy(d_src, mono.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
-    for (int v = 0; v < 3; v++) CK(cudaMalloc(&d_dst[v], (size_t)N * 8));
+    for (int v = 0; v < 4; v++) CK(cudaMalloc(&d_dst[v], (size_t)N * 8));
     rc = do_convert(c, d_src, d_dst, 0, 1, 0);
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("transform of X failed"); rc = BMI_ECUDA; }
     std::vector<u64> pts(N);
     std::vector<u32> expo(N);
-    for (int v = 0; v < 3 && !rc; v++) {
+    for (int v = 0; v < 4 && !rc; v++) {
         if (!c->d_bskp[v]) continue;
         if (cudaMemcpy(pts.data(), d_dst[v], (size_t)N * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy of transform of X failed"); rc = BMI_ECUDA; break; }
         for (int u = 0; u < N; u++) {
@@ -181,14 +215,14 @@ int bmi_ctx_load_bsk_pairs(bmi_ctx* c, const uint64_t* h_bskp) {
         if (cudaMemcpy(c->d_expo[v], expo.data(), (size_t)N * 4, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("upload of exponents failed"); rc = BMI_ECUDA; }
     }
     cudaFree(d_src);
-    for (int v = 0; v < 3; v++) cudaFree(d_dst[v]);
+    for (int v = 0; v < 4; v++) cudaFree(d_dst[v]);
     if (!rc) c->pairs = true;
     return rc;
 }
 
 int bmi_ctx_load_ksk(bmi_ctx* c, const uint64_t* h_ksk) {
     if (!c || !h_ksk) { set_error("null argument"); return BMI_EINVAL; }
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     const size_t bytes = (size_t)c->p.k * c->p.N * c->p.ksk_l * (c->p.n + 1) * 8;
     if (!c->d_ksk) CK(cudaMalloc(&c->d_ksk, bytes));
     CK(cudaMemcpy(c->d_ksk, h_ksk, bytes, cudaMemcpyHostToDevice));
@@ -202,7 +236,7 @@ int bmi_ctx_load_ksk(bmi_ctx* c, const uint64_t* h_ksk) {
 
 int bmi_ctx_load_luts(bmi_ctx* c, const uint64_t* h_luts, int32_t n_luts) {
     if (!c || !h_luts || n_luts < 1) { set_error("invalid argument"); return BMI_EINVAL; }
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     cudaFree(c->d_luts);
     c->d_luts = nullptr;
     CK(cudaMalloc(&c->d_luts, (size_t)n_luts * c->p.N * 8));
@@ -220,7 +254,8 @@ int bmi_ctx_set_tma_stage(bmi_ctx* c, int32_t on) {
 }
 
 int bmi_ctx_set_pbs_mode(bmi_ctx* c, int32_t mode) {
-    if (!c || mode < 0 || mode > 3) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (!c || mode < 0 || mode > 5 || mode == 4) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (mode == 5 && c->pairs && !c->d_bskp[3]) { set_error("select mode 5 before bmi_ctx_load_bsk_pairs: its key layout is built at load time"); return BMI_ESTATE; }
     c->pbs_mode = mode;
     return BMI_OK;
 }
@@ -229,6 +264,7 @@ int bmi_lincomb(bmi_ctx* c, const uint64_t* d_vals, const int32_t* d_row_ptr, co
                 const uint64_t* d_konst, uint64_t* d_out, int32_t njobs, int32_t batch, void* stream) {
     if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
     if (njobs == 0) return BMI_OK;
+    GUARD(c);
     const int W = c->p.k * c->p.N + 1;
     dim3 grid((unsigned)((int64_t)njobs * batch), (W + 2047) / 2048);
     lincomb_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_vals, d_row_ptr, d_idx, d_coef, d_konst, d_out, W, batch);
@@ -241,6 +277,7 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
     if (!c || count < 0) { set_error("invalid argument"); return BMI_EINVAL; }
     if (!c->d_ksk) { set_error("keyswitch key not loaded"); return BMI_ESTATE; }
     if (count == 0) return BMI_OK;
+    GUARD(c);
     const int cols = (c->p.n + 1 + KS_COLS - 1) / KS_COLS, tiles = (int)((count + KS_JT - 1) / KS_JT);
     const int kN = c->p.k * c->p.N;
     // enough CTAs for ~3 per SM: small batches split the input coefficients over blockIdx.z
@@ -256,7 +293,7 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
             c->ks_partial_cap = need;
         }
     }
-    dim3 grid(cols, tiles, slices);
+    dim3 grid(tiles, cols, slices);
     const size_t smem = (size_t)KS_CHUNK * c->p.ksk_l * KS_JT * sizeof(int);
     keyswitch_kernel<<<grid, KS_COLS, smem, (cudaStream_t)stream>>>(d_in, c->d_ksk, c->d_ks_corr, d_out, c->ks_partial, (int)count, kN, c->p.n,
                                                                    c->p.ksk_bl, c->p.ksk_l, slice);
@@ -277,6 +314,7 @@ int bmi_pbs(bmi_ctx* c, const uint64_t* d_small, const int32_t* d_job_in, const 
     if (!c || njobs < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
     if (!(c->d_bsk[0] || c->d_bsk[2] || c->pairs) || !c->d_luts) { set_error("bootstrapping key / LUTs not loaded"); return BMI_ESTATE; }
     if (njobs == 0) return BMI_OK;
+    GUARD(c);
     PbsArgs a;
     a.bsk_hat = nullptr; a.tw = c->d_tw; a.twi = c->d_twi; a.luts = c->d_luts; a.small = d_small;
     a.job_in = d_job_in; a.job_lut = d_job_lut; a.job_out = d_job_out; a.out = d_out;
@@ -288,7 +326,7 @@ int bmi_pbs(bmi_ctx* c, const uint64_t* d_small, const int32_t* d_job_in, const 
 int bmi_ks_pbs_host(bmi_ctx* c, const uint64_t* h_in, const int32_t* h_lut_idx, uint64_t* h_out, int64_t count) {
     if (!c || !h_in || !h_lut_idx || !h_out || count < 0) { set_error("invalid argument"); return BMI_EINVAL; }
     if (count == 0) return BMI_OK;
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     for (int64_t q = 0; q < count; q++)
         if (h_lut_idx[q] < 0 || h_lut_idx[q] >= c->n_luts) { set_error("LUT index out of range"); return BMI_EINVAL; }
     int rc = ensure_scratch(c, count);
@@ -305,7 +343,7 @@ int bmi_ks_pbs_host(bmi_ctx* c, const uint64_t* h_in, const int32_t* h_lut_idx, 
 
 int bmi_polymul_host(bmi_ctx* c, const uint64_t* h_a, const uint64_t* h_b, uint64_t* h_c, int32_t count) {
     if (!c || !h_a || !h_b || !h_c || count < 1) { set_error("invalid argument"); return BMI_EINVAL; }
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     const size_t bytes = (size_t)count * c->p.N * 8;
     u64 *a = nullptr, *b = nullptr, *o = nullptr;
     CK(cudaMalloc(&a, bytes)); CK(cudaMalloc(&b, bytes)); CK(cudaMalloc(&o, bytes));

@@ -14,29 +14,29 @@ struct PbsArgs {
     u64* __restrict__ out;             // [rows][N+1] big-key LWE
     int njobs, batch;
     int n, bl, l;
-    // pair blind rotation (two key bits per step): bsk_hat is then the pair key [n/2][3][2][2][N]
+    // pair blind rotation (two key bits per step): bsk_hat is then the pair key [n/2][K11, K11+K10, K11+K01][2][2][N]
     const u32* __restrict__ expo;      // [N] transform slot (in bsk_hat's layout) -> r with evaluation point psi^r
     const u64* __restrict__ pw;        // [2N] psi^t
 };
 
 // Pair blind rotation, transform domain: the GGSW the step multiplies the decomposed accumulator with is
-//   (X^(a1+a2) - 1) K11 + (X^a1 - 1) K10 + (X^a2 - 1) K01
-// and a monomial X^e is, at the slot whose evaluation point is psi^r, the scalar psi^(e r mod 2N).
+//   (X^(a1+a2) - 1) K11 + (X^a1 - 1) K10 + (X^a2 - 1) K01  =  m10 (m01 K11 + KA) + m01 KB,
+// m10 = X^a1 - 1, m01 = X^a2 - 1, KA = K11 + K10, KB = K11 + K01 (the sums are formed once when the key is loaded,
+// pair_key_sums_kernel), and a monomial X^e is, at the slot whose evaluation point is psi^r, the scalar
+// psi^(e r mod 2N).  Three products per slot and output polynomial.
 struct PairMono {
-    u64 m11, m10, m01;      // lazy
+    u64 m10, m01;      // lazy
 };
 __device__ __forceinline__ PairMono pair_monomials(const PbsArgs& a, u32 slot, u32 a1, u32 a2, u32 mask2n) {
     const u32 e = __ldg(a.expo + slot);
-    const u64 p10 = __ldg(a.pw + ((a1 * e) & mask2n)), p01 = __ldg(a.pw + ((a2 * e) & mask2n));
     PairMono m;
-    m.m11 = fsub_l(fmul_l(p10, p01), 1);
-    m.m10 = fsub_l(p10, 1);
-    m.m01 = fsub_l(p01, 1);
+    m.m10 = fsub_l(__ldg(a.pw + ((a1 * e) & mask2n)), 1);
+    m.m01 = fsub_l(__ldg(a.pw + ((a2 * e) & mask2n)), 1);
     return m;
 }
-// m11 k11 + m10 k10 + m01 k01, lazy
-__device__ __forceinline__ u64 pair_combine(const PairMono& m, u64 k11, u64 k10, u64 k01) {
-    return fadd_l(fadd_l(fmul_c(m.m11, k11), fmul_l(m.m10, k10)), fmul_c(m.m01, k01));
+// m10 (m01 k11 + ka) + m01 kb, lazy; the key words are canonical
+__device__ __forceinline__ u64 pair_combine(const PairMono& m, u64 k11, u64 ka, u64 kb) {
+    return fadd_l(fmul_l(m.m10, fadd_l(fmul_l(m.m01, k11), ka)), fmul_c(m.m01, kb));
 }
 
 // The two builds of the bootstrap kernel per polynomial size: coefficients per thread (log2) and the CTAs per SM

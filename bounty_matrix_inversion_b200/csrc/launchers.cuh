@@ -10,7 +10,7 @@
 
 #include "../../include/bmi_tfhe.h"
 #include "host_common.h"
-#include "split.cuh"
+#include "split2.cuh"
 
 using bmi_host::set_error;
 
@@ -31,8 +31,9 @@ struct bmi_ctx {
     u64* d_bsk[3] = {nullptr, nullptr, nullptr};   // transform-domain key: throughput build / latency build / 8-CTA split kernel
     // pair blind rotation (bmi_ctx_load_bsk_pairs): the pair key in the same three layouts, per layout the exponent of
     // every transform slot's evaluation point, and the powers of psi
-    u64* d_bskp[3] = {nullptr, nullptr, nullptr};
-    u32* d_expo[3] = {nullptr, nullptr, nullptr};
+    // [3]: two-points-per-thread 8-CTA kernel (split2.cuh), keys stored as K11, K11+K10, K11+K01
+    u64* d_bskp[4] = {nullptr, nullptr, nullptr, nullptr};
+    u32* d_expo[4] = {nullptr, nullptr, nullptr, nullptr};
     u64* d_pw = nullptr;
     bool pairs = false;
     int n_luts = 0;
@@ -41,7 +42,9 @@ struct bmi_ctx {
     int split_clusters = -1;   // resident 8-CTA clusters of the split kernel (queried once)
     bool split_async = true;  // split kernel synchronised by mbarriers + st.async (BMI_SPLIT_ASYNC=0: cluster barriers)
     bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
-    int pbs_mode = 0;   // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel
+    // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel,
+    // 5 8-CTA kernel with two points per thread and warp-shuffle stages (split2.cuh; measured slower, kept for A/B)
+    int pbs_mode = 0;
     // scratch for the host-buffer convenience path
     u64 *w_in = nullptr, *w_small = nullptr, *w_out = nullptr;
     int *w_idx = nullptr, *w_lut = nullptr;
@@ -56,6 +59,11 @@ constexpr int kMaxSmem = 227 * 1024;   // dynamic shared memory a CTA can opt in
 inline size_t pbs_smem(const bmi_ctx* c) { return (size_t)3 * c->p.N * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
 
 inline size_t split_smem(const bmi_ctx* c) { return (size_t)6 * (c->p.N / 4) * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
+// pair rotation: plus the 2N powers of psi up to N = 4096
+inline size_t split_smem_pairs(const bmi_ctx* c) { return split_smem(c) + (c->logN <= 12 ? (size_t)2 * c->p.N * 8 : 0); }
+template <int L>
+inline size_t split2_smem(const bmi_ctx* c) { return (size_t)Split2Cfg<L>::WORDS * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
+constexpr int kMaxSplit2L = 13;    // two points per thread: N/8 threads per CTA
 inline size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
 
 template <int L>
@@ -66,9 +74,13 @@ template <int L>
 int setup_attrs(const bmi_ctx* c) {
     CK(cudaFuncSetAttribute(pbs_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
     CK(cudaFuncSetAttribute(pbs_split_async_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
-    CK(cudaFuncSetAttribute(pbs_split_async_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem(c)));
+    CK(cudaFuncSetAttribute(pbs_split_async_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split_smem_pairs(c)));
     CK(cudaFuncSetAttribute(polymul_split_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SplitCfg<L>::M * 8));
     CK(cudaFuncSetAttribute(bsk_convert_split_kernel<L, split_convert_e<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    if constexpr (L <= kMaxSplit2L) {
+        CK(cudaFuncSetAttribute(pbs_split2_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)split2_smem<L>(c)));
+        CK(cudaFuncSetAttribute(bsk_convert_split2_kernel<L, split_convert_e<L>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
+    }
     if constexpr (L <= kMaxClusterL) {
         constexpr int TP = throughput_ctas_per_sm<L>(), EL = latency_e<L>(), ET = throughput_e<L>();
         const int sm = (int)pbs_smem(c), sms = (int)pbs_smem_staged(c);
@@ -102,6 +114,12 @@ int launch_convert(bmi_ctx* c, const u64* src, u64* const* dst, int64_t p0, int6
         constexpr int EC = split_convert_e<L>();
         bsk_convert_split_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, dst[2] + off, c->d_tw, c->ninv);
         c->launches++;
+        if constexpr (L <= kMaxSplit2L) {
+            if (dst[3]) {
+                bsk_convert_split2_kernel<L, EC><<<(unsigned)polys, NttCfg<L, EC>::T, (1 << L) * 8, st>>>(src, dst[3] + off, c->d_tw, c->ninv);
+                c->launches++;
+            }
+        }
     }
     CK(cudaGetLastError());
     return BMI_OK;
@@ -129,9 +147,18 @@ int64_t split_capacity(bmi_ctx* c) {
 
 template <int L>
 int launch_split(bmi_ctx* c, PbsArgs a, int64_t total, cudaStream_t st) {
+    if constexpr (L <= kMaxSplit2L) {
+        if (c->pairs && c->d_bskp[3] && c->pbs_mode == 5) {
+            a.bsk_hat = c->d_bskp[3]; a.expo = c->d_expo[3]; a.pw = c->d_pw;
+            pbs_split2_kernel<L><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), Split2Cfg<L>::T, split2_smem<L>(c), st>>>(a);
+            c->launches++;
+            CK(cudaGetLastError());
+            return BMI_OK;
+        }
+    }
     if (c->pairs) {
         a.bsk_hat = c->d_bskp[2]; a.expo = c->d_expo[2]; a.pw = c->d_pw;
-        pbs_split_async_kernel<L, true><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem(c), st>>>(a);
+        pbs_split_async_kernel<L, true><<<8 * (unsigned)std::min<int64_t>(total, 1 << 16), SplitCfg<L>::T, split_smem_pairs(c), st>>>(a);
         c->launches++;
         CK(cudaGetLastError());
         return BMI_OK;
@@ -160,7 +187,7 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
     const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
     // A handful of ciphertexts: spread each over an 8-CTA cluster (4 CTAs per polynomial), lowest latency.
-    if (one && (c->pbs_mode == 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) return launch_split<L>(c, a, total, st);
+    if (one && (c->pbs_mode >= 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) return launch_split<L>(c, a, total, st);
     const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
     a.bsk_hat = c->d_bsk[latency ? 1 : 0];
     const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);

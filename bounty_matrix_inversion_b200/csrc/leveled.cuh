@@ -27,8 +27,9 @@ __global__ void __launch_bounds__(KS_COLS) keyswitch_kernel(const u64* __restric
                                                             u64* __restrict__ partial, int M, int kN, int n, int bl, int l,
                                                             int slice) {
     extern __shared__ u32 dg[];   // [KS_CHUNK][l][KS_JT] shifted digits d' = d + B/2
-    const int tid = threadIdx.x, t = blockIdx.x * KS_COLS + tid;
-    const int job0 = blockIdx.y * KS_JT;
+    // ciphertext tiles along gridDim.x (2^31 - 1 blocks), output-column groups along y, input slices along z
+    const int tid = threadIdx.x, t = blockIdx.y * KS_COLS + tid;
+    const int job0 = blockIdx.x * KS_JT;
     const int njob = min(KS_JT, M - job0);
     const int tot = bl * l;
     const bool live = t <= n;
@@ -121,4 +122,16 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const u64* __restrict__ va
         }
         o[w] = s;
     }
+}
+
+// ----------------------------------------------------------------------------
+// pair key, transform domain, any layout: [pair][K11, K10, K01][2 rows][2 outputs][N] -> [pair][K11, K11+K10, K11+K01][..]
+__global__ void __launch_bounds__(256) pair_key_sums_kernel(u64* __restrict__ key, size_t per_pair_third, size_t pairs) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per_pair_third * pairs) return;
+    const size_t q = e / per_pair_third, w = e % per_pair_third;
+    u64* base = key + q * 3 * per_pair_third + w;
+    const u64 k11 = base[0];
+    base[per_pair_third] = fadd(k11, base[per_pair_third]);
+    base[2 * per_pair_third] = fadd(k11, base[2 * per_pair_third]);
 }

@@ -225,8 +225,11 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
 //  same time, more DSMEM traffic -- not kept.)
 // PAIR: two key bits per step with the pair key (kernels.cuh).  The accumulator itself is decomposed, so no CTA reads
 // another CTA's accumulator and the acc_bar round disappears along with half of the steps.
+#ifndef BMI_SPLIT_MINB
+#define BMI_SPLIT_MINB 1
+#endif
 template <int L, bool PAIR = false>
-__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) pbs_split_async_kernel(const PbsArgs a) {
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, BMI_SPLIT_MINB) pbs_split_async_kernel(const PbsArgs a) {
     using C = SplitCfg<L>;
     using LC = typename C::Local;
     constexpr int N = C::N, M = C::M, T = C::T;
@@ -236,7 +239,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
     u64* gbuf = smem + 2 * M;
     u64* lbuf = smem + 3 * M;
     u64* recv = smem + 4 * M;         // [2][M]
-    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 6 * M);
+    constexpr bool PW_SMEM = PAIR && L <= 12;  // the 2N powers of psi in shared memory (32 KB at N = 2048)
+    u64* pws = smem + 6 * M;
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 6 * M + (PW_SMEM ? 2 * N : 0));
     __shared__ __align__(8) u64 bars[4];      // acc, fwd, rcv, inv
     const int tid = threadIdx.x;
     const u32 rank = cluster_rank(), c = rank >> 2, r = rank & 3, group0 = c << 2, partner = ((c ^ 1) << 2) + r;
@@ -249,8 +254,21 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
         mbar_init(&bars[2], 1);
         mbar_init(&bars[3], 1);
     }
+    if constexpr (PW_SMEM)
+        for (int i = tid; i < 2 * N; i += T) pws[i] = __ldg(a.pw + i);
     __syncthreads();
     cluster_sync_all();               // every CTA's barriers exist before anyone signals them
+    // per-thread constants of the whole kernel: the twiddles of the two block stages, and (pair rotation) the
+    // exponents of this thread's four transform slots
+    const int blk = (int)r * T + tid;
+    const u64 cwa = __ldg(a.tw + (1 << (L - 2)) + blk), cwb0 = __ldg(a.tw + (1 << (L - 1)) + 2 * blk), cwb1 = __ldg(a.tw + (1 << (L - 1)) + 2 * blk + 1);
+    const u64 ciwa = __ldg(a.twi + (1 << (L - 2)) + blk), ciwb0 = __ldg(a.twi + (1 << (L - 1)) + 2 * blk), ciwb1 = __ldg(a.twi + (1 << (L - 1)) + 2 * blk + 1);
+    u32 ex[4] = {0, 0, 0, 0};
+    if constexpr (PAIR) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) ex[e] = __ldg(a.expo + (u32)r * M + e * T + tid);
+    }
+    const u64* pwt = PW_SMEM ? pws : a.pw;
     u32 gbuf_r[4], lbuf_r[4], fwd_bar_r[4], inv_bar_r[4], acc_bar_r[4];
 #pragma unroll
     for (int g = 0; g < 4; g++) {
@@ -321,14 +339,10 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
                 const ulonglong2 v23 = *reinterpret_cast<const ulonglong2*>(gbuf + tid * 4 + 2);
                 x[0] = v01.x; x[1] = v01.y; x[2] = v23.x; x[3] = v23.y;
             }
-            const int blk = (int)r * T + tid;
-            {
-                const u64 wa = __ldg(a.tw + (1 << (L - 2)) + blk);
-                butterfly<false>(x[0], x[2], wa);
-                butterfly<false>(x[1], x[3], wa);
-                butterfly<false>(x[0], x[1], __ldg(a.tw + (1 << (L - 1)) + 2 * blk));
-                butterfly<false>(x[2], x[3], __ldg(a.tw + (1 << (L - 1)) + 2 * blk + 1));
-            }
+            butterfly<false>(x[0], x[2], cwa);
+            butterfly<false>(x[1], x[3], cwa);
+            butterfly<false>(x[0], x[1], cwb0);
+            butterfly<false>(x[2], x[3], cwb1);
             // ---- pointwise products; the partner polynomial's share goes to the partner CTA
             u64 own[4];
             const u32 rbase = recv_r + (ph ? (u32)M * 8 : 0);
@@ -338,7 +352,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int idx = e * T + tid;
-                    const PairMono m = pair_monomials(a, (u32)r * M + idx, at, at2, 2 * N - 1);
+                    PairMono m;
+                    m.m10 = fsub_l(pwt[(at * ex[e]) & (2 * N - 1)], 1);
+                    m.m01 = fsub_l(pwt[(at2 * ex[e]) & (2 * N - 1)], 1);
                     const size_t oc = (size_t)(c ^ 1) * N + idx, mc = (size_t)c * N + idx;
                     const u64 ko = pair_combine(m, __ldg(gp + oc), __ldg(gp + 4 * N + oc), __ldg(gp + 8 * N + oc));
                     st_async_u64(rbase + (u32)idx * 8, fmul_c(x[e], ko), rcv_bar_r);
@@ -360,13 +376,10 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(SplitCfg<L>::T, 1) p
                 for (int e = 0; e < 4; e++) own[e] = fadd_l(own[e], rb[e * T + tid]);
             }
             // ---- inverse: two block stages, all-to-all, local stages
-            butterfly<true>(own[0], own[1], __ldg(a.twi + (1 << (L - 1)) + 2 * blk));
-            butterfly<true>(own[2], own[3], __ldg(a.twi + (1 << (L - 1)) + 2 * blk + 1));
-            {
-                const u64 wa = __ldg(a.twi + (1 << (L - 2)) + blk);
-                butterfly<true>(own[0], own[2], wa);
-                butterfly<true>(own[1], own[3], wa);
-            }
+            butterfly<true>(own[0], own[1], ciwb0);
+            butterfly<true>(own[2], own[3], ciwb1);
+            butterfly<true>(own[0], own[2], ciwa);
+            butterfly<true>(own[1], own[3], ciwa);
 #pragma unroll
             for (int e = 0; e < 4; e++) st_async_u64(lbuf_r[e] + (u32)blk * 8, own[e], inv_bar_r[e]);
             mbar_wait(&bars[3], ph);

@@ -84,7 +84,9 @@ int bmi_ctx_load_luts(bmi_ctx* ctx, const uint64_t* h_luts, int32_t n_luts);   /
 int64_t bmi_ctx_launch_count(const bmi_ctx* ctx);            /* kernels launched by this context so far */
 /* bootstrap kernel build: 0 = automatic (picked per launch size), 1 = latency build (4 or 8 coefficients per thread:
  * most warps per transform), 2 = throughput build, 3 = 8-CTA cluster per ciphertext (each polynomial over 4 SMs; one
- * decomposition level only); bmi_polymul_host follows the same choice */
+ * decomposition level only), 5 = the 8-CTA kernel with two points per thread and warp-shuffle butterflies (pair key
+ * only; select it BEFORE bmi_ctx_load_bsk_pairs; measured slower than 3, kept for comparison);
+ * bmi_polymul_host follows the same choice */
 int bmi_ctx_set_pbs_mode(bmi_ctx* ctx, int32_t mode);
 /* 1 = bring each CMUX's GGSW rows into shared memory with a TMA bulk copy issued one CMUX ahead (where it fits);
  * 0 (default) = per-thread coalesced global loads, measured 4-8 % faster on B200 */

@@ -27,6 +27,8 @@ all_ok = True
 for prm in (PR.TOY_1024_L1, PR.TOY_2048_L1, PR.TOY_4096, PR.TOY_8192_L1, PR.TOY_16384_L1):
     keys = native.ClientKeys(prm, seed=2024, pairs=True)
     eng = native.Engine(prm, 0)
+    if prm.N <= 8192:
+        eng.set_pbs_mode(5)          # builds the key layout of the two-points-per-thread kernel as well
     eng.load_keys(None, keys.ksk, bskp=keys.bskp)
     rng = np.random.default_rng(9)
     tables = [[(3 * m + 1) % 16 for m in range(8)], [m * m % 16 for m in range(8)]]
@@ -41,7 +43,7 @@ for prm in (PR.TOY_1024_L1, PR.TOY_2048_L1, PR.TOY_4096, PR.TOY_8192_L1, PR.TOY_
     lut_idx = np.array([0, 1, 0, 1, 1], np.int32)
     want = np.stack([orc.pbs_pairs(prm, keys.bskp, luts[lut_idx[i]], small[i]) for i in range(5)])
     dec_ok = [PR.decode(int(keys.phase(want[i])[0]), 4) == tables[lut_idx[i]][msgs[i]] for i in range(4)]
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 5):
         if prm.N > 8192 and mode != 3:
             continue
         eng.set_pbs_mode(mode)
