@@ -20,7 +20,8 @@ void set_error(const std::string& msg) { g_err = msg; }
     extern template int setup_attrs<L>(const bmi_ctx*);                                                  \
     extern template int launch_convert<L>(bmi_ctx*, const u64*, u64* const*, int64_t, int64_t, cudaStream_t); \
     extern template int launch_pbs<L>(bmi_ctx*, PbsArgs, cudaStream_t);                                  \
-    extern template int launch_polymul<L>(bmi_ctx*, const u64*, const u64*, u64*, int, cudaStream_t);
+    extern template int launch_polymul<L>(bmi_ctx*, const u64*, const u64*, u64*, int, cudaStream_t); \
+    extern template int64_t split_capacity<L>(bmi_ctx*);
 BMI_EXTERN_L(10) BMI_EXTERN_L(11) BMI_EXTERN_L(12) BMI_EXTERN_L(13) BMI_EXTERN_L(14)
 
 namespace {
@@ -53,6 +54,7 @@ struct DeviceGuard {
 int do_setup(bmi_ctx* c) { DISPATCH_L(c, setup_attrs<L>(c)); }
 int do_convert(bmi_ctx* c, const u64* s, u64* const* dst, int64_t p0, int64_t polys, cudaStream_t st) { DISPATCH_L(c, launch_convert<L>(c, s, dst, p0, polys, st)); }
 int do_pbs(bmi_ctx* c, const PbsArgs& a, cudaStream_t st) { DISPATCH_L(c, launch_pbs<L>(c, a, st)); }
+int64_t do_capacity(bmi_ctx* c) { DISPATCH_L(c, split_capacity<L>(c)); }
 int do_polymul(bmi_ctx* c, const u64* a, const u64* b, u64* o, int n, cudaStream_t st) { DISPATCH_L(c, launch_polymul<L>(c, a, b, o, n, st)); }
 
 // upload a standard-domain key of `polys` polynomials in slices through a bounded staging buffer, converting slice by
@@ -271,6 +273,25 @@ int bmi_lincomb(bmi_ctx* c, const uint64_t* d_vals, const int32_t* d_row_ptr, co
     c->launches++;
     CK(cudaGetLastError());
     return BMI_OK;
+}
+
+int bmi_scatter_rows(bmi_ctx* c, const uint64_t* d_src, const int32_t* d_dst_row, uint64_t* d_dst, int32_t count, int32_t batch, void* stream) {
+    if (!c || count < 0 || batch < 1) { set_error("invalid argument"); return BMI_EINVAL; }
+    if (count == 0) return BMI_OK;
+    GUARD(c);
+    const int W = c->p.k * c->p.N + 1;
+    dim3 grid((unsigned)((int64_t)count * batch), (W + 2047) / 2048);
+    scatter_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, d_dst_row, d_dst, W, batch);
+    c->launches++;
+    CK(cudaGetLastError());
+    return BMI_OK;
+}
+
+int32_t bmi_ctx_pbs_capacity(bmi_ctx* c) {
+    if (!c) return 0;
+    if (c->p.bsk_l != 1) return 0;
+    DeviceGuard guard(c->device);
+    return (int32_t)do_capacity(c);
 }
 
 int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t count, void* stream) {

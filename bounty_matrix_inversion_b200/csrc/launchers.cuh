@@ -39,7 +39,8 @@ struct bmi_ctx {
     int n_luts = 0;
     int num_sms = 148;
     int64_t launches = 0;
-    int split_clusters = -1;   // resident 8-CTA clusters of the split kernel (queried once)
+    int split_clusters[2] = {-1, -1};   // resident 8-CTA clusters of the split kernel, single / pair rotation (queried once)
+    int latency_resident = -1;          // CTAs per SM of the latency build (queried once)
     bool split_async = true;  // split kernel synchronised by mbarriers + st.async (BMI_SPLIT_ASYNC=0: cluster barriers)
     bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
     // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel,
@@ -128,21 +129,24 @@ int launch_convert(bmi_ctx* c, const u64* src, u64* const* dst, int64_t p0, int6
 // how many 8-CTA clusters of the split kernel the GPU keeps resident at once (cluster placement is per GPC)
 template <int L>
 int64_t split_capacity(bmi_ctx* c) {
-    if (c->split_clusters < 0) {
+    int& cached = c->split_clusters[c->pairs ? 1 : 0];      // of the kernel launch_split actually launches
+    if (cached < 0) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(8 * 64);
         cfg.blockDim = dim3(SplitCfg<L>::T);
-        cfg.dynamicSmemBytes = split_smem(c);
+        cfg.dynamicSmemBytes = c->pairs ? split_smem_pairs(c) : split_smem(c);
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 8; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, pbs_split_kernel<L>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = c->num_sms / 10; }
-        c->split_clusters = n;
+        const cudaError_t e = c->pairs ? cudaOccupancyMaxActiveClusters(&n, pbs_split_async_kernel<L, true>, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&n, pbs_split_async_kernel<L, false>, &cfg);
+        if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = c->num_sms / 10; }
+        cached = n;
     }
-    return c->split_clusters;
+    return cached;
 }
 
 template <int L>
@@ -182,10 +186,13 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     const unsigned grid = 2 * (unsigned)std::min<int64_t>(total, 1 << 20);      // one CTA pair per ciphertext
     // While the launch fits the CTA pairs the latency build keeps resident, latency wins; beyond one wave the
     // 16-coefficients-per-thread build (fewer shared-memory round trips, more ciphertexts per SM) does.
-    int resident = 1;
-    if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true, false>, NttCfg<L, EL>::T, pbs_smem(c));
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
-    const int64_t one_wave = (int64_t)std::max(resident, 1) * c->num_sms / 2;
+    if (c->latency_resident < 0) {
+        int resident = 1;
+        if (one) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, true, false>, NttCfg<L, EL>::T, pbs_smem(c));
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pbs_cluster_kernel<L, EL, 1, false, false>, NttCfg<L, EL>::T, pbs_smem(c));
+        c->latency_resident = std::max(resident, 1);
+    }
+    const int64_t one_wave = (int64_t)c->latency_resident * c->num_sms / 2;
     // A handful of ciphertexts: spread each over an 8-CTA cluster (4 CTAs per polynomial), lowest latency.
     if (one && (c->pbs_mode >= 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) return launch_split<L>(c, a, total, st);
     const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);

@@ -135,3 +135,14 @@ __global__ void __launch_bounds__(256) pair_key_sums_kernel(u64* __restrict__ ke
     base[per_pair_third] = fadd(k11, base[per_pair_third]);
     base[2 * per_pair_third] = fadd(k11, base[2 * per_pair_third]);
 }
+
+// ----------------------------------------------------------------------------
+// rows of W words: dst[dst_row[j] * batch + b] = src[j * batch + b]  (all-gathered bootstrap outputs -> value slots)
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const u64* __restrict__ src, const int* __restrict__ dst_row,
+                                                           u64* __restrict__ dst, int W, int batch) {
+    const int f = blockIdx.x;
+    const int j = f / batch, b = f - j * batch;
+    const u64* s = src + (size_t)f * W;
+    u64* d = dst + ((size_t)dst_row[j] * batch + b) * W;
+    for (int w = blockIdx.y * blockDim.x + threadIdx.x; w < W; w += gridDim.y * blockDim.x) d[w] = s[w];
+}

@@ -1,7 +1,15 @@
 """GPU execution of a levelled Program through the C ABI (one launch group per level).
 
-PyTorch only owns device memory and streams here; every arithmetic step is a kernel of
-libbmi_tfhe.so (bmi_lincomb -> bmi_keyswitch -> bmi_pbs).
+PyTorch only owns device memory, streams and the process group here; every arithmetic step is a kernel of
+libbmi_tfhe.so (bmi_lincomb -> bmi_keyswitch -> bmi_pbs, plus bmi_scatter_rows after an all-gather).
+
+* The program is re-levelled for the engine's launch capacity first (fhe/schedule.py): lookups with slack leave
+  levels that would exceed what one bootstrap launch handles at minimum latency.
+* The whole static program is captured once per batch size as a CUDA graph and replayed (thousands of launches
+  become one submission); `graphs=False` keeps the eager per-level loop.
+* world > 1 (one process per GPU, keys replicated): rank r bootstraps a contiguous share of every level's lookups
+  -- and keyswitches only the rows those lookups read -- straight into its slice of a gather buffer; one in-place
+  NCCL all-gather per level, then a row scatter into the value slots.
 """
 from __future__ import annotations
 
@@ -11,6 +19,7 @@ import torch
 from .. import params as PR
 from ..native import Engine
 from .program import Program
+from .schedule import rebalance
 
 P = PR.P
 
@@ -29,12 +38,21 @@ def shard_bounds(n_jobs: int, rank: int, world: int):
 
 class Executor:
     def __init__(self, program: Program, params: PR.TfheParams, engine: Engine, device: int = 0,
-                 rank: int = 0, world: int = 1, group=None, torch_device=None):
-        """engine: anything with load_luts / lincomb / keyswitch / pbs taking torch tensors (native.Engine on a GPU;
-        the CPU tests of the multi-rank plumbing inject a clear-text stand-in).  rank/world/group: level sharding."""
-        self.prog, self.params, self.eng = program, params, engine
+                 rank: int = 0, world: int = 1, group=None, torch_device=None, level_capacity="auto", graphs=True):
+        """engine: anything with load_luts / lincomb / keyswitch / pbs / scatter_rows taking torch tensors
+        (native.Engine on a GPU; the CPU tests of the multi-rank plumbing inject a clear-text stand-in).
+        rank/world/group: level sharding.  level_capacity: lookups per level the scheduler aims for ("auto": what the
+        engine reports per GPU, times world; 0 / None: keep the program's own levels)."""
+        self.params, self.eng = params, engine
         self.dev = torch.device("cuda", device) if torch_device is None else torch.device(torch_device)
         self.rank, self.world, self.group = rank, world, group
+        if level_capacity == "auto":
+            level_capacity = int(getattr(engine, "pbs_capacity", 0)) * world
+        # every program goes through the scheduler: with no capacity it only normalises the level layout (lookups of
+        # a level ordered by keyswitch row, which the sharded path relies on)
+        program = rebalance(program, int(level_capacity) if level_capacity else 1 << 30)
+        self.prog = program
+        self.level_capacity = int(level_capacity or 0)
         W1 = getattr(engine, "words", params.big_dim + 1)
         self.W1 = W1
         # a clear-text stand-in engine computes in half-message units (Program.tables_half_units)
@@ -57,9 +75,22 @@ class Executor:
         self.d_idx = t(cat([l.idx for l in lv], np.int32))
         self.d_coef = t(_field(cat([l.coef for l in lv], np.int64)))
         self.d_konst = t(_field(cat([l.konst for l in lv], np.int64), scale))
-        self.d_job_ks = t(cat([l.job_ks for l in lv], np.int32))
         self.d_job_lut = t(cat([l.job_lut for l in lv], np.int32))
         self.d_job_out = t(cat([l.job_out for l in lv], np.int32))
+        # per level: this rank's lookups [lo, hi), the keyswitch rows [r0, r1) they read, and the lookups' rows
+        # relative to r0
+        self.shard = []
+        local_ks = []
+        for l in lv:
+            per, lo, hi = shard_bounds(len(l.job_ks), rank, world)
+            if hi > lo:
+                assert np.all(np.diff(l.job_ks) >= 0), "lookups of a level must be ordered by keyswitch row"
+                r0, r1 = int(l.job_ks[lo]), int(l.job_ks[hi - 1]) + 1
+            else:
+                r0 = r1 = 0
+            self.shard.append((per, lo, hi, r0, r1))
+            local_ks.append(l.job_ks - (r0 if world > 1 else 0))
+        self.d_job_ks = t(cat(local_ks, np.int32))
         self.d_out_ptr = t(program.out_row_ptr.astype(np.int32))
         self.d_out_idx = t(program.out_idx.astype(np.int32))
         self.d_out_coef = t(_field(program.out_coef))
@@ -69,6 +100,9 @@ class Executor:
         self._batch = 0
         self.stream = None           # torch.cuda.Stream for every launch of this executor (None = current stream)
         self.profile = None          # list of (start event, end event, jobs) around every PBS launch when profiling
+        self.graphs = bool(graphs) and self.dev.type == "cuda"
+        self._graph = None           # (batch, torch.cuda.CUDAGraph)
+        self.level_events = None     # with collect_level_times(): CUDA events around lincomb+keyswitch / PBS / exchange
 
     def collect_profile(self, origin=None):
         """PBS-kernel time measured with CUDA events on the launching stream, and the algorithmic work it covers;
@@ -80,15 +114,7 @@ class Executor:
         ms = sum(a.elapsed_time(b) for a, b, _ in prof)
         jobs = sum(j for _, _, j in prof)
         per_pbs_bytes = p.bsk_bytes() + (p.n + 1) * 8 + p.N * 8 + (p.big_dim + 1) * 8
-        butterflies = (p.k + 1) * (p.bsk_l + 1) * (p.N // 2) * p.logN
-        per_step = butterflies * 26 + (p.k + 1) ** 2 * p.bsk_l * p.N * 22 + (p.k + 1) * p.bsk_l * p.N * 12
-        if p.bsk_group == 2:
-            # pair key: per slot and CTA one product + three subtractions for the monomials, six products + four
-            # additions to combine the three keys for both output polynomials, two products with the digits
-            per_step = butterflies * 26 + (p.k + 1) * p.N * (9 * 22 + 7 * 3) + (p.k + 1) * p.bsk_l * p.N * 12
-        per_pbs_int = (p.n // p.bsk_group) * per_step
-        out = {"pbs_ms": ms, "pbs_launches": len(prof), "pbs_jobs": jobs, "alg_bytes": jobs * per_pbs_bytes,
-               "int_ops": jobs * per_pbs_int}
+        out = {"pbs_ms": ms, "pbs_launches": len(prof), "pbs_jobs": jobs, "alg_bytes": jobs * per_pbs_bytes}
         if origin is not None:
             out["intervals"] = [(origin.elapsed_time(a), origin.elapsed_time(b)) for a, b, _ in prof]
         return out
@@ -97,6 +123,7 @@ class Executor:
         if batch == self._batch:
             return
         p = self.params
+        self._graph = None
         self.vals = torch.zeros((self.prog.n_slots, batch, self.W1), dtype=torch.int64, device=self.dev)
         self.ks_in = torch.empty((self.max_ks * batch, self.W1), dtype=torch.int64, device=self.dev)
         self.small = torch.empty((self.max_ks * batch, getattr(self.eng, "small_words", p.n + 1)), dtype=torch.int64, device=self.dev)
@@ -104,8 +131,7 @@ class Executor:
         self.outs = torch.empty((n_out, batch, self.W1), dtype=torch.int64, device=self.dev)
         if self.world > 1:
             rows = shard_bounds(self.max_pbs, 0, self.world)[0] * self.world       # padded so every rank owns `per` rows
-            self.stage = torch.empty((rows, batch, self.W1), dtype=torch.int64, device=self.dev)
-            self.mine = torch.empty((rows // self.world, batch, self.W1), dtype=torch.int64, device=self.dev)
+            self.stage = torch.zeros((rows, batch, self.W1), dtype=torch.int64, device=self.dev)
             self.iota = torch.arange(rows, dtype=torch.int32, device=self.dev)
         self._batch = batch
 
@@ -118,66 +144,123 @@ class Executor:
         batch = x.shape[0]
         self._ensure(batch)
         host = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2)).view(np.int64))
-        self.vals[: self.prog.n_inputs].copy_(host, non_blocking=True)
-        self.run_device(batch)
-        out = self.outs.cpu().numpy().view(np.uint64).transpose(1, 0, 2)
+        with self._on_stream():
+            self.vals[: self.prog.n_inputs].copy_(host, non_blocking=True)
+            self.run_device(batch)
+            out = self.outs.cpu()
+        out = out.numpy().view(np.uint64).transpose(1, 0, 2)
         return out[0] if single else np.ascontiguousarray(out)
+
+    # ---- streams: every torch op of this executor runs on the same stream as its kernels
+    def _s(self):
+        if self.dev.type != "cuda":
+            return None
+        return self.stream if self.stream is not None else torch.cuda.current_stream(self.dev)
+
+    def _on_stream(self):
+        import contextlib
+        if self.dev.type != "cuda" or self.stream is None:
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self.stream)
 
     def run_device(self, batch):
         """inputs already in self.vals[:n_inputs]; leaves output ciphertexts in self.outs"""
+        if not self.graphs or self.profile is not None or self.level_events is not None:
+            return self._issue(batch)
+        if self._graph is None or self._graph[0] != batch:
+            self._capture(batch)
+        if self._graph[1] is None:       # capture was not possible on this setup: eager loop
+            return self._issue(batch)
+        with self._on_stream():
+            self._graph[1].replay()
+
+    def _capture(self, batch):
+        # value slots are reused by liveness, so a run overwrites its own inputs: keep them across the warm-up run
+        inputs = self.vals[: self.prog.n_inputs].clone()
+        self._issue(batch)               # warm-up: lazy allocations and occupancy queries happen outside the capture
+        torch.cuda.synchronize(self.dev)
+        self.vals[: self.prog.n_inputs].copy_(inputs)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.dev)
+        keep, self.stream = self.stream, side
+        try:
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.graph(g, stream=side):
+                self._issue(batch)
+            self._graph = (batch, g)
+        except Exception:                # noqa: BLE001 -- e.g. a collective that cannot be captured: fall back to eager
+            torch.cuda.synchronize(self.dev)
+            self._graph = (batch, None)
+        finally:
+            self.stream = keep
+        torch.cuda.synchronize(self.dev)
+
+    def _issue(self, batch):
         eng, prog = self.eng, self.prog
         for li in range(len(prog.levels)):
             self._level(li, batch)
         eng.lincomb(self.vals, self.d_out_ptr, self.d_out_idx, self.d_out_coef, self.d_out_konst, self.outs,
                     len(prog.out_konst), batch, stream=self._s())
 
-    def _s(self):
-        if self.dev.type != "cuda":
-            return None
-        return self.stream if self.stream is not None else torch.cuda.current_stream(self.dev)
+    def _mark(self, st):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(st)
+        return e
 
     def _level(self, li, batch):
         eng = self.eng
         st = self._s()
-        k0, k1 = self.ks_off[li], self.ks_off[li + 1]
+        k0 = self.ks_off[li]
         p0, p1 = self.pbs_off[li], self.pbs_off[li + 1]
-        n_ks, n_pbs = int(k1 - k0), int(p1 - p0)
+        n_pbs = int(p1 - p0)
         if n_pbs == 0:
             return
-        # this level's CSR rows index the concatenated idx/coef arrays through their own row_ptr (level-local offsets)
-        rp = self.d_row_ptr[self.rp_off[li]: self.rp_off[li + 1]]
-        idx = self.d_idx[self.nz_off[li]: self.nz_off[li + 1]]
-        coef = self.d_coef[self.nz_off[li]: self.nz_off[li + 1]]
-        konst = self.d_konst[k0:k1]
-        job_ks, job_lut, job_out = self.d_job_ks[p0:p1], self.d_job_lut[p0:p1], self.d_job_out[p0:p1]
+        per, lo, hi, r0, r1 = self.shard[li]
+        n_rows = r1 - r0
+        ev = [self._mark(st)] if self.level_events is not None else None
+        if hi > lo:
+            # this level's CSR rows index the concatenated idx/coef arrays through their own row_ptr (level-local
+            # offsets); a rank forms and keyswitches only the rows [r0, r1) its lookups read
+            rp = self.d_row_ptr[self.rp_off[li] + r0: self.rp_off[li] + r1 + 1]
+            idx = self.d_idx[self.nz_off[li]: self.nz_off[li + 1]]
+            coef = self.d_coef[self.nz_off[li]: self.nz_off[li + 1]]
+            konst = self.d_konst[k0 + r0: k0 + r1]
+            eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_rows, batch, stream=st)
+            eng.keyswitch(self.ks_in, self.small, n_rows * batch, stream=st)
+        if ev is not None:
+            ev.append(self._mark(st))
+        job_ks, job_lut = self.d_job_ks[p0 + lo: p0 + hi], self.d_job_lut[p0 + lo: p0 + hi]
         if self.world == 1:
-            eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch, stream=st)
-            eng.keyswitch(self.ks_in, self.small, n_ks * batch, stream=st)
+            job_out = self.d_job_out[p0:p1]
             if self.profile is not None:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(st)
+                a = self._mark(st)
                 eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch, stream=st)
-                b.record(st)
-                self.profile.append((a, b, n_pbs * batch))
+                self.profile.append((a, self._mark(st), n_pbs * batch))
             else:
                 eng.pbs(self.small, job_ks, job_lut, job_out, self.vals, n_pbs, batch, stream=st)
+            if ev is not None:
+                ev.append(self._mark(st))
+                self.level_events.append((n_pbs, ev))
             return
-        self._level_sharded(li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs)
-
-    # ---- one box, several GPUs: each rank bootstraps a contiguous share of the level's lookups, then the
-    # output ciphertexts are all-gathered over NVLink (keys are replicated on every GPU)
-    def _level_sharded(self, li, batch, rp, idx, coef, konst, job_ks, job_lut, job_out, n_ks, n_pbs):
+        # ---- one box, several GPUs: bootstrap my share straight into my slice of the gather buffer, all-gather in
+        # place over NVLink, scatter the level's outputs into their value slots
         import torch.distributed as dist
-        eng = self.eng
-        per, lo, hi = shard_bounds(n_pbs, self.rank, self.world)
-        # every rank forms all keyswitch inputs it needs; for simplicity all rows (cheap next to the bootstraps)
-        st = self._s()
-        eng.lincomb(self.vals, rp, idx, coef, konst, self.ks_in, n_ks, batch, stream=st)
-        eng.keyswitch(self.ks_in, self.small, n_ks * batch, stream=st)
         stage = self.stage[: per * self.world]
         if hi > lo:
-            eng.pbs(self.small, job_ks[lo:hi], job_lut[lo:hi], self.iota[lo:hi], stage, hi - lo, batch, stream=st)
-        mine = stage[self.rank * per: (self.rank + 1) * per]
-        self.mine[:per].copy_(mine)                       # all_gather needs an input that does not alias the output
-        dist.all_gather_into_tensor(stage, self.mine[:per], group=self.group)
-        self.vals.index_copy_(0, job_out.long(), stage[:n_pbs])
+            eng.pbs(self.small, job_ks, job_lut, self.iota[lo:hi], stage, hi - lo, batch, stream=st)
+        if ev is not None:
+            ev.append(self._mark(st))
+        with self._on_stream():
+            dist.all_gather_into_tensor(stage, stage[self.rank * per: (self.rank + 1) * per], group=self.group)
+        eng.scatter_rows(stage, self.d_job_out[p0:p1], self.vals, n_pbs, batch, stream=st)
+        if ev is not None:
+            ev.append(self._mark(st))
+            self.level_events.append((n_pbs, ev))
+
+    def collect_level_times(self):
+        """(lookups, ms lincomb+keyswitch, ms bootstrap, ms exchange) per level of the last eager run"""
+        torch.cuda.synchronize(self.dev)
+        out = []
+        for n_pbs, ev in self.level_events or []:
+            out.append((n_pbs, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]) if len(ev) > 3 else 0.0))
+        return out

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "bmi_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "bmi_ctx_set_pbs_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "bmi_ctx_set_tma_stage": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bmi_scatter_rows": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]),
+    "bmi_ctx_pbs_capacity": (C.c_int32, [C.c_void_p]),
     "bmi_lincomb": (C.c_int, [C.c_void_p] * 7 + [C.c_int32, C.c_int32, C.c_void_p]),
     "bmi_keyswitch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bmi_pbs": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p]),
@@ -208,7 +210,8 @@ class Engine:
         self.n_luts = luts.shape[0]
 
     def set_pbs_mode(self, mode: int):
-        """bootstrap kernel build: 0 automatic per launch size, 1 latency build, 2 throughput build, 3 8-CTA split kernel"""
+        """bootstrap kernel build: 0 automatic per launch size, 1 latency build, 2 throughput build, 3 8-CTA split kernel,
+        5 the 8-CTA kernel with two points per thread and warp-shuffle stages (select before load_keys)"""
         _check(lib().bmi_ctx_set_pbs_mode(self._h, mode))
 
     def set_tma_stage(self, on: bool):
@@ -223,6 +226,14 @@ class Engine:
     def lincomb(self, vals, row_ptr, idx, coef, konst, out, njobs, batch=1, stream=None):
         _check(lib().bmi_lincomb(self._h, vals.data_ptr(), row_ptr.data_ptr(), idx.data_ptr(), coef.data_ptr(),
                                  konst.data_ptr(), out.data_ptr(), njobs, batch, _stream(stream)))
+
+    def scatter_rows(self, src, dst_row, dst, count, batch=1, stream=None):
+        _check(lib().bmi_scatter_rows(self._h, src.data_ptr(), dst_row.data_ptr(), dst.data_ptr(), count, batch, _stream(stream)))
+
+    @property
+    def pbs_capacity(self) -> int:
+        """ciphertexts one bootstrap launch handles at its minimum latency (0: no low-latency kernel for this set)"""
+        return int(lib().bmi_ctx_pbs_capacity(self._h))
 
     def keyswitch(self, big, small, count, stream=None):
         _check(lib().bmi_keyswitch(self._h, big.data_ptr(), small.data_ptr(), count, _stream(stream)))

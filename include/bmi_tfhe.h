@@ -96,6 +96,12 @@ int bmi_ctx_set_tma_stage(bmi_ctx* ctx, int32_t on);
  * CSR: d_row_ptr [njobs+1] int32, d_idx int32 (row of d_vals before batch expansion), d_coef uint64 field elements */
 int bmi_lincomb(bmi_ctx* ctx, const uint64_t* d_vals, const int32_t* d_row_ptr, const int32_t* d_idx,
                 const uint64_t* d_coef, const uint64_t* d_konst, uint64_t* d_out, int32_t njobs, int32_t batch, void* stream);
+/* rows of k*N+1 words: d_dst row d_dst_row[j]*batch+b <- d_src row j*batch+b (e.g. all-gathered bootstrap outputs of
+ * a level into their value slots) */
+int bmi_scatter_rows(bmi_ctx* ctx, const uint64_t* d_src, const int32_t* d_dst_row, uint64_t* d_dst, int32_t count, int32_t batch, void* stream);
+/* how many ciphertexts one bmi_pbs launch bootstraps at its minimum latency (the 8-CTA clusters this GPU keeps resident);
+ * 0 when the parameter set has no such kernel.  The host-side scheduler sizes circuit levels with it. */
+int32_t bmi_ctx_pbs_capacity(bmi_ctx* ctx);
 /* count big-key LWEs [count][k*N+1] -> small-key LWEs [count][n+1] */
 int bmi_keyswitch(bmi_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, int64_t count, void* stream);
 /* njobs*batch bootstraps: job q, lane b reads d_small row job_in[q]*batch+b, applies LUT job_lut[q],

@@ -49,6 +49,9 @@ class ClearEngine:
             t = self.tables[job_lut[q].item(), torch.where(m >= self.size, m - self.size, m)]
             o[job_out[q].item(), :, 0] = torch.where(m >= self.size, -t, t)
 
+    def scatter_rows(self, src, dst_row, dst, count, batch=1, stream=None):
+        dst.view(-1, batch, 1)[dst_row[:count].long()] = src.view(-1, batch, 1)[:count]
+
 
 def _messages(half_units, width):
     """what decryption returns: the signed message mod 2^(width+1)"""
@@ -62,11 +65,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, path, ret):
+def _worker(rank, world, port, path, capacity, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     z, prog = np.load(path), Program.load(path)
-    ex = Executor(prog, PR.TOY_1024, ClearEngine(prog.width), rank=rank, world=world, torch_device="cpu")
+    ex = Executor(prog, PR.TOY_1024, ClearEngine(prog.width), rank=rank, world=world, torch_device="cpu", level_capacity=capacity)
+    if capacity:
+        over = lambda p: sum(len(l.job_ks) > capacity for l in p.levels)
+        assert over(ex.prog) < over(prog) and len(ex.prog.levels) == len(prog.levels) and ex.prog.n_pbs == prog.n_pbs
     x = z["golden_inputs"].astype(np.int64)[:3]
     batch = x.shape[0]
     ex._ensure(batch)
@@ -79,12 +85,13 @@ def _worker(rank, world, port, path, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_level_sharded_execution_over_gloo(world):
+@pytest.mark.parametrize("world,capacity", [(2, 0), (3, 0), (2, 6)])
+def test_level_sharded_execution_over_gloo(world, capacity):
+    """capacity > 0: the levels are re-balanced for that many lookups per level first (fhe/schedule.py)"""
     path = os.path.join(HERE, "golden", "qf_add_medium.npz")
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), path, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), path, capacity, ret), nprocs=world, join=True)
     assert dict(ret) == {r: True for r in range(world)}
 
 
