@@ -21,7 +21,10 @@ class Configuration:
     multiplication ("auto" | "quarter_square", see tracing.Trace),
     split_wide ("auto" | True | False), split_guard and collapse_borrows (see program.lower),
     blind_rotation ("pairs" | "single"): two key bits per bootstrap step with the pair key (default wherever the
-    parameter set has one decomposition level and an even LWE dimension), or one GGSW per key bit"""
+    parameter set has one decomposition level and an even LWE dimension), or one GGSW per key bit,
+    level_capacity ("auto" | int | 0): lookups per circuit level the run-time scheduler aims for (fhe/schedule.py;
+    auto = what the engine bootstraps at minimum latency, per GPU and batch lane), cuda_graphs (replay the program as
+    one CUDA graph, default True)"""
 
     def __init__(self, **options):
         self.options = dict(options)
@@ -35,6 +38,8 @@ class Configuration:
         self.split_guard = options.get("split_guard")
         self.collapse_borrows = options.get("collapse_borrows", True)
         self.blind_rotation = options.get("blind_rotation", "pairs")
+        self.level_capacity = options.get("level_capacity", "auto")
+        self.cuda_graphs = options.get("cuda_graphs", True)
         if self.blind_rotation not in ("pairs", "single"):
             raise ValueError("blind_rotation must be 'pairs' or 'single'")
 
@@ -194,7 +199,9 @@ class Circuit:
         return outs[0] if len(outs) == 1 else tuple(outs)
 
     # ---- server
-    def executor(self, rank=0, world=1, group=None, device=None):
+    def executor(self, rank=0, world=1, group=None, device=None, lanes=1):
+        """lanes: independent evaluations per run (batch lanes); the level scheduler divides the engine's launch
+        capacity by it"""
         if self._executor is None:
             from ..native import Engine
             from .executor import Executor
@@ -202,11 +209,15 @@ class Circuit:
             dev = self.cfg.device if device is None else device
             eng = Engine(self.params, dev)
             eng.load_keys(self.keys.bsk, self.keys.ksk, bskp=self.keys.bskp)
-            self._executor = Executor(self.program, self.params, eng, dev, rank, world, group)
+            capacity = self.cfg.level_capacity
+            if capacity == "auto":
+                capacity = eng.pbs_capacity * world // max(1, lanes)
+            self._executor = Executor(self.program, self.params, eng, dev, rank, world, group, level_capacity=capacity,
+                                      graphs=self.cfg.cuda_graphs)
         return self._executor
 
     def run(self, encrypted: EncryptedData) -> EncryptedData:
-        out = self.executor().run(encrypted.cts)
+        out = self.executor(lanes=encrypted.cts.shape[0] if encrypted.batch else 1).run(encrypted.cts)
         return EncryptedData(out, encrypted.batch)
 
     def encrypt_run_decrypt(self, *args):
