@@ -103,11 +103,11 @@ CASES = {
     "inv2_low_quarter_square": lambda: inversion_case(2, "low"),       # compiled with Concrete's two-lookup product lowering
     "inv2_low_prefix": lambda: inversion_case(2, "low"),               # borrow chains by parallel prefix (latency-oriented)
     "inv2_medium": lambda: inversion_case(2, "medium"),
-    "inv3_low": lambda: inversion_case(3, "low", n_golden=4),
-    "inv3_low_prefix": lambda: inversion_case(3, "low", n_golden=4),
-    "inv3_medium": lambda: inversion_case(3, "medium", n_golden=2),
-    "inv4_high": lambda: inversion_case(4, "high", n_golden=2),
-    "inv4_high_prefix": lambda: inversion_case(4, "high", n_golden=2),
+    "inv3_low": lambda: inversion_case(3, "low", n_golden=8),
+    "inv3_low_prefix": lambda: inversion_case(3, "low", n_golden=8),
+    "inv3_medium": lambda: inversion_case(3, "medium", n_golden=8),
+    "inv4_high": lambda: inversion_case(4, "high", n_golden=8),
+    "inv4_high_prefix": lambda: inversion_case(4, "high", n_golden=8),
     "qf_add_medium": lambda: qfloat_op_case("add", "medium"),
     "qf_sub_medium": lambda: qfloat_op_case("sub", "medium"),
     "qf_mul_medium": lambda: qfloat_op_case("mul", "medium"),
