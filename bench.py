@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=32, help="inv3_medium_batch: independent inversions per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profile runs of the full 4,096-pair workload)")
     ap.add_argument("--inversion", default="auto", help="also time one encrypted inversion: 2 | 3 | 4 (low precision), a "
                                                        "compiled program in tests/golden (e.g. inv3_medium, inv4_high_prefix), "
                                                        "none, or auto = inv3_low_prefix (levels sharded over the GPUs)")
@@ -324,11 +325,11 @@ def run_microbench(args, fhe, PR, torch, dist, local, rank, world):
     t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(1 if args.no_e2e else args.steps):
         outs = step_e2e()
     e1.record()
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3)
+    e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) * (args.steps if args.no_e2e else 1)
 
     # correctness of what was just timed: decrypt lanes 0..3 of the last end-to-end step and compare with the
     # clear evaluation of the same compiled program (itself pinned to the reference's clear path by tests/golden)

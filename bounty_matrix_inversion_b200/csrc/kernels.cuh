@@ -134,6 +134,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, u32 byte
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
+// (A suspend-time hint on try_wait was measured: no change in either bootstrap kernel, so the plain form stays.)
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     asm volatile("{ .reg .pred p;\n"
                  "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"

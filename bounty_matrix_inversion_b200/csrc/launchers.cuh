@@ -193,9 +193,21 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
         c->latency_resident = std::max(resident, 1);
     }
     const int64_t one_wave = (int64_t)c->latency_resident * c->num_sms / 2;
+    // Automatic choice: the build with the smallest estimated time for this launch size.  Measured on B200 at N = 2048
+    // with the pair rotation (profiles/r2_pbs_sweep_pairs_w4.jsonl): one wave of the 8-CTA kernel 2.5 ms, one wave of
+    // the latency build 4.3 ms, the throughput build 9.4 ms up to half a GPU of ciphertexts and 0.05 ms per ciphertext
+    // beyond; the ratios carry over to the other sizes.
+    int pick = c->pbs_mode;
+    if (pick == 0) {
+        const int64_t cap = one ? split_capacity<L>(c) : 0;
+        const double t_split = cap > 0 ? (double)((total + cap - 1) / cap) : 1e30;
+        const double t_lat = 1.72 * (double)((total + one_wave - 1) / one_wave);
+        const double t_tp = std::max(3.76, 0.0199 * (double)total);
+        pick = t_split <= t_lat && t_split <= t_tp ? 3 : (t_lat <= t_tp ? 1 : 2);
+    }
     // A handful of ciphertexts: spread each over an 8-CTA cluster (4 CTAs per polynomial), lowest latency.
-    if (one && (c->pbs_mode >= 3 || (c->pbs_mode == 0 && total <= split_capacity<L>(c)))) return launch_split<L>(c, a, total, st);
-    const bool latency = c->pbs_mode == 1 || (c->pbs_mode == 0 && total <= one_wave);
+    if (one && pick >= 3) return launch_split<L>(c, a, total, st);
+    const bool latency = pick == 1;
     a.bsk_hat = c->d_bsk[latency ? 1 : 0];
     const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
     if (c->pairs) {

@@ -92,7 +92,18 @@ class Program:
     def save(self, path, **extra):
         """compiled programs travel as .npz (the compile step needs the circuit's Python source; running does not)"""
         lv = self.levels
-        cat = lambda xs, dt: np.concatenate([np.asarray(x, dt) for x in xs]) if xs else np.zeros(0, dt)
+
+        def cat(xs, dt):
+            """concatenate and narrow to the on-disk type; a value that does not fit is an error, never a wrap-around"""
+            if not xs:
+                return np.zeros(0, dt)
+            wide = np.concatenate([np.asarray(x, np.int64) for x in xs])
+            if dt is not bool and wide.size:
+                info = np.iinfo(dt)
+                if wide.min() < info.min or wide.max() > info.max:
+                    raise OverflowError(f"program field out of range for {np.dtype(dt).name}: [{wide.min()}, {wide.max()}]")
+            return wide.astype(dt)
+
         np.savez_compressed(
             path, width=self.width, n_inputs=self.n_inputs, n_slots=self.n_slots, input_slots=self.input_slots,
             ks_counts=np.array([len(l.konst) for l in lv], np.int64), nz_counts=np.array([len(l.idx) for l in lv], np.int64),

@@ -187,3 +187,40 @@ def test_errors(setup, native):
         eng.ks_pbs_host(keys.encrypt([0]), np.array([99], np.int32))   # LUT index out of range
     with pytest.raises(native.NativeError):
         native.Engine(PR.TfheParams("bad", 10, 2, 1024, 8, 3, 4, 5, 1.0, 1.0), 0)   # k != 1
+
+
+def test_keyswitch_batch_beyond_65535_tiles(native, oracle):
+    """more ciphertext tiles than gridDim.y holds (8 x 65535 rows): the tiles run along gridDim.x.  The batch is 13
+    distinct random ciphertexts repeated, so every output row must equal the oracle's keyswitch of its source row."""
+    import torch
+    prm = PR.TOY_1024
+    keys = native.ClientKeys(prm, seed=3, evaluation_keys=True)
+    eng = native.Engine(prm, 0)
+    eng.load_keys(keys.bsk, keys.ksk)
+    rng = np.random.default_rng(17)
+    base = rand_field(rng, (13, prm.big_dim + 1))
+    count = 8 * 65535 + 9
+    big = dev(base).repeat((count + 12) // 13, 1)[:count].contiguous()
+    small = torch.zeros((count, prm.n + 1), dtype=torch.int64, device="cuda")
+    eng.keyswitch(big, small, count)
+    torch.cuda.synchronize()
+    want = np.stack([oracle.keyswitch(prm, keys.ksk, base[i]) for i in range(13)])
+    got = small.view(-1, prm.n + 1)
+    want_dev = dev(want)
+    idx = torch.arange(count, device="cuda") % 13
+    assert bool(torch.equal(got, want_dev[idx]))
+    eng.close()
+
+
+def test_scatter_rows(native):
+    import torch
+    prm = PR.TOY_1024
+    eng = native.Engine(prm, 0)
+    W = prm.big_dim + 1
+    src = torch.arange(5 * 3 * W, dtype=torch.int64, device="cuda").view(5, 3, W)
+    dst = torch.zeros((9, 3, W), dtype=torch.int64, device="cuda")
+    rows = torch.tensor([7, 0, 3, 8, 1], dtype=torch.int32, device="cuda")
+    eng.scatter_rows(src, rows, dst, 5, batch=3)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(dst[rows.long()], src)) and int(dst[2].abs().sum()) == 0
+    eng.close()

@@ -48,3 +48,13 @@ def test_forced_lookups_are_never_delayed():
     new = rebalance(prog, 1)
     assert len(new.levels) == len(prog.levels)
     assert np.array_equal(new.evaluate_clear(x[:2]), want[:2])
+
+
+def test_program_save_refuses_values_that_do_not_fit(tmp_path):
+    prog, _x, _w = _load("qf_add_medium")
+    prog.save(str(tmp_path / "ok.npz"))
+    back = Program.load(str(tmp_path / "ok.npz"))
+    assert all(np.array_equal(a.coef, b.coef) and np.array_equal(a.job_lut, b.job_lut) for a, b in zip(prog.levels, back.levels))
+    prog.levels[0].coef[0] = 2 ** 40
+    with pytest.raises(OverflowError):
+        prog.save(str(tmp_path / "bad.npz"))
