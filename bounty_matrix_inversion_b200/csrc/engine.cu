@@ -140,6 +140,7 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* v = getenv("BMI_TMA_STAGE")) c->tma_stage = v[0] == '1';
     if (const char* v = getenv("BMI_SPLIT_ASYNC")) c->split_async = v[0] != '0';
+    if (const char* v = getenv("BMI_KS_CTAS_PER_SM")) c->ks_ctas_per_sm = std::max(1, atoi(v));
     int rc = ctx_init_device(c);
     if (rc) { bmi_ctx_destroy(c); return rc; }      // nothing allocated so far outlives a failed create
     *out = c;
@@ -301,8 +302,8 @@ int bmi_keyswitch(bmi_ctx* c, const uint64_t* d_in, uint64_t* d_out, int64_t cou
     GUARD(c);
     const int cols = (c->p.n + 1 + KS_COLS - 1) / KS_COLS, tiles = (int)((count + KS_JT - 1) / KS_JT);
     const int kN = c->p.k * c->p.N;
-    // enough CTAs for ~3 per SM: small batches split the input coefficients over blockIdx.z
-    int slices = std::max(1, std::min(kN / KS_CHUNK, (3 * c->num_sms) / std::max(1, cols * tiles)));
+    // enough CTAs for ks_ctas_per_sm per SM: batches split the input coefficients over blockIdx.z
+    int slices = std::max(1, std::min(kN / KS_CHUNK, (c->ks_ctas_per_sm * c->num_sms) / std::max(1, cols * tiles)));
     int slice = ((kN + slices - 1) / slices + KS_CHUNK - 1) / KS_CHUNK * KS_CHUNK;
     slices = (kN + slice - 1) / slice;
     if (slices > 1) {

@@ -1,12 +1,13 @@
 #!/bin/bash
-# Everything the DESIGN.md tables quote, in one GPU call (about 8 minutes on one B200):
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/measure_all.sh'
-# Results land in gpurun_out/measure_*.{log,jsonl,json}; copy what is to be tracked into profiles/.
+# Every single-GPU number DESIGN.md and README.md quote, in one call (about 10 minutes on one B200):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/measure_all.sh'
+# Results land in gpurun_out/r2_final_*; copy what is to be tracked into profiles/.
+# (8 GPUs: scripts/measure_8gpu.sh; N GPUs, inversions only: torchrun ... scripts/inversion_multi.py NAME ...)
 set -u
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/measure_gpu_tests.log 2>&1; tail -2 gpurun_out/measure_gpu_tests.log
-timeout 300 python scripts/inversion_time.py inv2_low inv2_low_prefix inv3_low inv3_low_prefix inv3_medium inv4_high inv4_high_prefix > gpurun_out/measure_inversions.jsonl 2> gpurun_out/measure_inversions.err
-cat gpurun_out/measure_inversions.jsonl
-timeout 60 python scripts/pair_check.py time > gpurun_out/measure_pair_check.jsonl 2>&1; tail -3 gpurun_out/measure_pair_check.jsonl
-timeout 120 python scripts/inversion_batch.py inv3_low 8 > gpurun_out/measure_batch8.jsonl 2> gpurun_out/measure_batch8.err; cat gpurun_out/measure_batch8.jsonl
-timeout 300 python bench.py > gpurun_out/measure_bench.json 2> gpurun_out/measure_bench.err; cat gpurun_out/measure_bench.json
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r2_final_gpu_tests.log 2>&1; tail -3 gpurun_out/r2_final_gpu_tests.log
+timeout 300 python bench.py > gpurun_out/r2_final_bench_1gpu.json 2> gpurun_out/r2_final_bench_1gpu.err; tail -c 700 gpurun_out/r2_final_bench_1gpu.json
+timeout 300 python scripts/inversion_multi.py inv2_low inv2_low_prefix inv3_low inv3_low_prefix inv3_medium inv4_high inv4_high_prefix > gpurun_out/r2_final_inversions_1gpu.jsonl 2> gpurun_out/r2_final_inversions_1gpu.err
+cat gpurun_out/r2_final_inversions_1gpu.jsonl | cut -c1-330
+SWEEP_PAIRS=1 SWEEP_MODES=0,1,2,3 SWEEP_COUNTS=1,8,16,33,74,148,296,592,1184,2368 timeout 200 python scripts/pbs_sweep.py w4 > gpurun_out/r2_final_sweep_pairs_w4.jsonl 2> gpurun_out/r2_final_sweep.err
+timeout 400 python bench.py --workload inv3_medium_batch --lanes 32 --steps 1 > gpurun_out/r2_final_inv3_medium_batch_1gpu.json 2> gpurun_out/r2_final_inv3_medium_batch_1gpu.err; cat gpurun_out/r2_final_inv3_medium_batch_1gpu.json | cut -c1-900
