@@ -3,7 +3,7 @@
 `program.lower` places every lookup at the earliest level its inputs allow (as soon as possible).  The critical path of
 the reference's inversions is long and thin, while a few levels hold hundreds of lookups that are
 not needed for many levels to come.  A bootstrap launch costs the same from one ciphertext up to the number of
-ciphertexts the low-latency kernel keeps resident (36 on one B200 at N = 2048), so lookups with slack are moved into
+ciphertexts the low-latency kernel keeps resident (33 on one B200 at N = 2048), so lookups with slack are moved into
 later, emptier levels: same lookups, same number of levels, the same results bit for bit (every lookup still reads the
 same values), fewer launches beyond the resident capacity.
 
@@ -11,6 +11,8 @@ The pass works on the Program itself (levels, CSR rows over value slots), so it 
 and can be redone for another capacity (another GPU, or `world` GPUs sharing each level).
 """
 from __future__ import annotations
+
+import heapq
 
 import numpy as np
 
@@ -79,11 +81,9 @@ def rebalance(prog: Program, capacity: int = 36, tiers=None) -> Program:
     # list scheduling, least slack first; a level takes everything that can wait no longer, then fills up to the
     # smallest tier that holds those
     size = np.array([len(g["jobs"]) for g in groups], np.int64)
-    pending = np.array([sum(1 for v in g["deps"] if v >= n_in and True) for g in groups], np.int64)
-    # count distinct producing groups rather than values
+    # a group becomes ready once every GROUP that produces one of its inputs has been scheduled
     pending = np.array([len({producer[v] for v in g["deps"] if v >= n_in}) for g in groups], np.int64)
     cons_groups = [sorted(set(c)) for c in consumers]
-    import heapq
     ready = [(int(alap[gi]), gi) for gi in range(len(groups)) if pending[gi] == 0]
     heapq.heapify(ready)
     level_of = np.zeros(len(groups), np.int64)
