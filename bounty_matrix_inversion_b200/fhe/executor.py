@@ -19,7 +19,7 @@ import torch
 from .. import params as PR
 from ..native import Engine
 from .program import Program
-from .schedule import rebalance
+from .schedule import schedule_for
 
 P = PR.P
 
@@ -50,7 +50,7 @@ class Executor:
             level_capacity = int(getattr(engine, "pbs_capacity", 0)) * world
         # every program goes through the scheduler: with no capacity it only normalises the level layout (lookups of
         # a level ordered by keyswitch row, which the sharded path relies on)
-        program = rebalance(program, int(level_capacity) if level_capacity else 1 << 30)
+        program = schedule_for(program, int(level_capacity or 0), world)
         self.prog = program
         self.level_capacity = int(level_capacity or 0)
         W1 = getattr(engine, "words", params.big_dim + 1)

@@ -54,6 +54,46 @@ def default_tiers(capacity: int):
     return [capacity * m for m in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 64, 128, 1 << 20)]
 
 
+def modelled_ms(prog: Program, capacity: int, world: int = 1) -> float:
+    """rough wall time of a run, for choosing between level layouts: per level, the bootstrap launch of the busiest rank
+    plus the fixed keyswitch / exchange cost.  Constants measured on B200 at N = 2048 with the pair rotation
+    (profiles/r2_pbs_sweep_pairs_w4.jsonl), expressed through the engine's launch capacity so that they carry over:
+    up to a quarter of the capacity 2.08 ms, up to about half 2.38, up to the capacity 2.48, then the wider builds."""
+    cap = max(capacity // max(world, 1), 1)
+    total = 0.0
+    for lv in prog.levels:
+        c = -(-len(lv.job_ks) // world)
+        if c <= max(cap // 4, 1):
+            t = 2.08
+        elif c <= max((cap * 18) // 33, 1):
+            t = 2.38
+        elif c <= cap:
+            t = 2.48
+        elif c <= (cap * 74) // 33:
+            t = 4.32
+        elif c <= 3 * cap:
+            t = 7.3
+        elif c <= (cap * 148) // 33:
+            t = 8.6
+        else:
+            t = max(9.4, 0.0496 * c)
+        total += t + 0.12
+    return total
+
+
+def schedule_for(prog: Program, capacity: int, world: int = 1) -> Program:
+    """the cheaper (modelled) of two layouts: levels filled up to the launch capacity, or first up to a quarter of it --
+    the size a launch still runs at its very lowest latency -- which pays once several GPUs share each level"""
+    if capacity <= 0:
+        return rebalance(prog, 1 << 30)
+    full = rebalance(prog, capacity)
+    quarter = (capacity // max(world, 1)) // 4 * world          # every rank still within a quarter of its own capacity
+    if world < 2 or quarter < 1:
+        return full
+    fine = rebalance(prog, capacity, [quarter] + default_tiers(capacity))
+    return fine if modelled_ms(fine, capacity, world) < modelled_ms(full, capacity, world) else full
+
+
 def rebalance(prog: Program, capacity: int = 36, tiers=None) -> Program:
     """move lookups with slack out of levels that exceed a launch-size tier into later levels with room.
     capacity: ciphertexts a bootstrap launch handles at its minimum latency (per GPU times the GPUs sharing a level)."""

@@ -58,3 +58,20 @@ def test_program_save_refuses_values_that_do_not_fit(tmp_path):
     prog.levels[0].coef[0] = 2 ** 40
     with pytest.raises(OverflowError):
         prog.save(str(tmp_path / "bad.npz"))
+
+
+def test_layout_choice_for_several_gpus():
+    """with several GPUs sharing each level the scheduler may stop filling at a quarter of the per-GPU capacity (the size
+    a launch runs at its lowest latency); whichever layout it picks, it is the cheaper one by its own model and the
+    same circuit"""
+    from bounty_matrix_inversion_b200.fhe.schedule import modelled_ms, schedule_for
+    prog, x, want = _load("inv3_low_prefix")
+    for world in (1, 2, 8):
+        cap = 33 * world
+        new = schedule_for(prog, cap, world)
+        assert len(new.levels) == len(prog.levels) and new.n_pbs == prog.n_pbs
+        assert modelled_ms(new, cap, world) <= modelled_ms(rebalance(prog, cap), cap, world) + 1e-9
+        assert modelled_ms(new, cap, world) < modelled_ms(prog, cap, world)
+    assert max(len(l.job_ks) for l in new.levels) <= 8 * 8          # 8 GPUs: every rank at most 8 lookups per level
+    assert np.array_equal(new.evaluate_clear(x[:1]), want[:1])
+    assert len(schedule_for(prog, 0, 1).levels) == len(prog.levels)
