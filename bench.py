@@ -163,19 +163,22 @@ def run_reference(args, rank, world):
     progs = load_programs()
     for _ in range(args.warmup):
         cpu_sample(progs, threads, seconds_hint=2.0)
+    # each step is a bounded sample; its size shrinks if the requested number of steps would not fit the time budget
+    left = args.time_budget - (time.time() - args.t_start) - 20.0
+    per_step = max(3.0, min(args.cpu_seconds, left / max(args.steps, 1) - 3.0))
     t0 = time.time()
     rates, done, which = [], 0, ""
     for _ in range(args.steps):
-        r, d, _s, which = cpu_sample(progs, threads, seconds_hint=args.cpu_seconds)
+        r, d, _s, which = cpu_sample(progs, threads, seconds_hint=per_step)
         rates.append(r)
         done += d
     wall = time.time() - t0
     value = float(np.mean(rates))
-    cfg = workload_config(progs, args.pairs, world)
-    cfg["note"] = ("concrete-python (the reference's FHE runtime) is not installable here; this arm times the CPU restatement "
-                   "of the same keyswitch+PBS path (oracle/tfhe_oracle_fast.c, -O3 -march=native, built on this host) on the "
-                   "workload's parameter sets, each step a bounded sample of the workload's lookups")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": args.gpus, "steps": args.steps,
+    cfg = workload_config(progs, args.pairs, world)              # identical to the GPU arm's `config`
+    note = ("concrete-python (the reference's FHE runtime) is not installable here; this arm times the CPU restatement "
+            "of the same keyswitch+PBS path (oracle/tfhe_oracle_fast.c, -O3 -march=native, built on this host) on the "
+            "workload's parameter sets, each step a bounded sample of the workload's lookups")
+    line = {"impl": "reference", "note": note, "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 (mod 2^64-2^32+1)", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": threads, "kind": "port",
@@ -204,10 +207,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profile runs of the full 4,096-pair workload)")
+    ap.add_argument("--time-budget", type=float, default=560.0, help="seconds the whole run aims to stay within: the host-buffer "
+                    "(e2e) pass repeats the step as often as the remaining time allows (at least twice, at most --steps)")
     ap.add_argument("--inversion", default="auto", help="also time one encrypted inversion: 2 | 3 | 4 (low precision), a "
                                                        "compiled program in tests/golden (e.g. inv3_medium, inv4_high_prefix), "
                                                        "none, or auto = inv3_low_prefix (levels sharded over the GPUs)")
     args = ap.parse_args()
+    args.t_start = time.time()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -321,15 +327,23 @@ def run_microbench(args, fhe, PR, torch, dist, local, rank, world):
     for op in OPS:
         circuits[op]._executor.profile = None
 
+    # the host-buffer pass repeats the same step; how often is bounded by the time the run has left (the inversion and
+    # the CPU sample still need about 100 s), identically on every rank
+    left = args.time_budget - (time.time() - args.t_start) - 100.0
+    e2e_steps = 1 if args.no_e2e else int(max(2, min(args.steps, left / max(dev_ms / args.steps * 1e-3, 1e-3))))
+    if world > 1:
+        agreed = torch.tensor([e2e_steps], dtype=torch.int64, device="cuda")
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        e2e_steps = int(agreed.item())
     barrier()
     t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(1 if args.no_e2e else args.steps):
+    for _ in range(e2e_steps):
         outs = step_e2e()
     e1.record()
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) * (args.steps if args.no_e2e else 1)
+    e2e_ms = max(e0.elapsed_time(e1), (time.time() - t0) * 1e3) * (args.steps / e2e_steps)
 
     # correctness of what was just timed: decrypt lanes 0..3 of the last end-to-end step and compare with the
     # clear evaluation of the same compiled program (itself pinned to the reference's clear path by tests/golden)
@@ -404,10 +418,11 @@ def run_microbench(args, fhe, PR, torch, dist, local, rank, world):
             "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 (mod 2^64-2^32+1)", "data": "synthetic",
-            "config": dict(workload_config(progs, P, world), params=bench_params,
-                           l2="bootstrapping keys (74 MB per op) plus keyswitch keys and value store exceed what stays resident "
-                              "across the three programs; each step re-streams all three key sets"),
-            "e2e": {"value": total / e2e_ms * 1e3, "unit": "PBS/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "config": dict(workload_config(progs, P, world), params=bench_params),
+            "l2_note": "bootstrapping keys (74 MB per op) plus keyswitch keys and value store exceed what stays resident across "
+                       "the three programs; each step re-streams all three key sets",
+            "e2e": {"value": total / e2e_ms * 1e3, "unit": "PBS/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps_timed": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "int_pipe", "kernel": "pbs_cluster_kernel<11,3,4,1,0,1> (throughput build, pair rotation)",
