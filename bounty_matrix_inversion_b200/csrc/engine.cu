@@ -138,7 +138,7 @@ int bmi_ctx_create(const bmi_params* p, int device, bmi_ctx** out) {
     c->p = *p; c->device = device; c->logN = logN;
     c->ninv = fpow((u64)p->N, BMI_P - 2);
     cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
-    if (const char* v = getenv("BMI_TMA_STAGE")) c->tma_stage = v[0] == '1';
+    if (const char* v = getenv("BMI_TMA_STAGE")) c->tma_stage = c->tma_stage_pairs = v[0] == '1';
     if (const char* v = getenv("BMI_SPLIT_ASYNC")) c->split_async = v[0] != '0';
     if (const char* v = getenv("BMI_KS_CTAS_PER_SM")) c->ks_ctas_per_sm = std::max(1, atoi(v));
     int rc = ctx_init_device(c);
@@ -252,7 +252,7 @@ int64_t bmi_ctx_launch_count(const bmi_ctx* c) { return c ? c->launches : 0; }
 
 int bmi_ctx_set_tma_stage(bmi_ctx* c, int32_t on) {
     if (!c) { set_error("invalid argument"); return BMI_EINVAL; }
-    c->tma_stage = on != 0;
+    c->tma_stage = c->tma_stage_pairs = on != 0;
     return BMI_OK;
 }
 

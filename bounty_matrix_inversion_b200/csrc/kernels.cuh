@@ -135,6 +135,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, u32 byte
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 // (A suspend-time hint on try_wait was measured: no change in either bootstrap kernel, so the plain form stays.)
+// bulk copy counted on `bar` without an arrival of its own (several copies behind one mbar_expect)
+__device__ __forceinline__ void tma_copy_1d(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
     asm volatile("{ .reg .pred p;\n"
                  "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
@@ -166,21 +171,23 @@ __device__ __forceinline__ void mbar_wait_cluster(u64* bar, u32 parity) {
                  "@p bra DC;\n bra WC;\n DC: }" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-//   STAGE     (ONE_LEVEL only) the two GGSW row polynomials of the next CMUX are brought into shared memory by one
-//             TMA bulk copy issued a whole CMUX ahead, instead of per-thread global loads after the transform
-//   PAIR      (ONE_LEVEL, no STAGE) two key bits per step with the pair key: the accumulator itself is decomposed (no
+//   STAGE     (ONE_LEVEL only) the GGSW row polynomials of the next step are brought into shared memory by TMA bulk
+//             copies issued a whole step ahead (2N words; with PAIR the three keys of the pair, 6N words), instead of
+//             per-thread global loads after the transform.  An A/B option (bmi_ctx_set_tma_stage), off by default.
+//   PAIR      (ONE_LEVEL) two key bits per step with the pair key: the accumulator itself is decomposed (no
 //             rotated reads), one forward/inverse transform serves both bits, the monomials enter the pointwise stage
 template <int L, int E, int MINB, bool ONE_LEVEL, bool STAGE, bool PAIR = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MINB) pbs_cluster_kernel(const PbsArgs a) {
-    static_assert(!PAIR || (ONE_LEVEL && !STAGE), "pair blind rotation: one decomposition level, no TMA staging");
+    static_assert(!PAIR || ONE_LEVEL, "pair blind rotation: one decomposition level");
+    constexpr int STAGE_WORDS = STAGE ? (PAIR ? 6 : 2) * NttCfg<L, E>::N : 0;
     using C = NttCfg<L, E>;
     constexpr int N = C::N, T = C::T, EPT = C::EPT;
     extern __shared__ u64 smem[];
     u64* acc = smem;                  // [N] this CTA's accumulator polynomial (canonical values)
     u64* buf = smem + N;              // [N] transform exchange buffer (swizzled)
     u64* recv = smem + 2 * N;         // [N] partial sums pushed by the partner CTA
-    u64* stage = smem + 3 * N;        // [2N] GGSW rows of the coming CMUX (STAGE only)
-    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + (STAGE ? 5 : 3) * N);   // [n] switched mask
+    u64* stage = smem + 3 * N;        // [2N | 6N] GGSW rows of the coming step (STAGE only)
+    unsigned short* rot = reinterpret_cast<unsigned short*>(smem + 3 * N + STAGE_WORDS);   // [n] switched mask
     __shared__ __align__(8) u64 stage_bar;
     const int tid = threadIdx.x;
     const u32 me = cluster_rank(), other = me ^ 1;
@@ -203,6 +210,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
     if (tid == 0) mbar_arrive_remote(peer_free_bar);      // the partner's first push needs no waiting
     // thread 0: start the bulk copy of the rows of the first CMUX at or after `from` that is not skipped
     auto prefetch_rows = [&](int from) {
+        if (PAIR) {
+            for (int i = from; i < n; i += 2)
+                if ((rot[i] | rot[i + 1]) != 0) {     // [pair][K11, KA, KB][row = me][both output polynomials][N]
+                    mbar_expect(&stage_bar, 6 * N * 8);
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        tma_copy_1d(stage + k * 2 * N, a.bsk_hat + ((size_t)(i >> 1) * 6 + k * 2 + me) * 2 * N, 2 * N * 8, &stage_bar);
+                    return;
+                }
+            return;
+        }
         for (int i = from; i < n; i++)
             if (rot[i] != 0) {
                 tma_load_1d(stage, a.bsk_hat + ((size_t)i * 2 + me) * 2 * N, 2 * N * 8, &stage_bar);
@@ -242,17 +260,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
                 for (int q = 0; q < EPT; q++) x[q] = digit_of(round_top(acc[q * T + tid], tot), bl, 1, 1);
                 ntt_forward<L, E>(x, buf, a.tw, tid);
                 mbar_wait_cluster(&xbar[1], ph_x);     // partner has consumed what I pushed for the previous step
-                // pair key: [pair][K11, K10, K01][row = decomposed polynomial][output polynomial][N]
+                // pair key: [pair][K11, KA, KB][row = decomposed polynomial][output polynomial][N]
                 const u64* gp = a.bsk_hat + ((size_t)(i >> 1) * 6 + me) * 2 * N;
+                if (STAGE) {
+                    mbar_wait(&stage_bar, stage_phase);
+                    stage_phase ^= 1;
+                }
 #pragma unroll
                 for (int q = 0; q < EPT; q++) {
                     const int idx = q * T + tid;
                     const PairMono m = pair_monomials(a, idx, at, at2, 2 * N - 1);
-                    const u64 ko = pair_combine(m, __ldg(gp + other * N + idx), __ldg(gp + 4 * N + other * N + idx),
-                                                __ldg(gp + 8 * N + other * N + idx));
+                    u64 ko, km;
+                    if (STAGE) {      // stage: [key][output polynomial][N]
+                        ko = pair_combine(m, stage[other * N + idx], stage[2 * N + other * N + idx], stage[4 * N + other * N + idx]);
+                        km = pair_combine(m, stage[me * N + idx], stage[2 * N + me * N + idx], stage[4 * N + me * N + idx]);
+                    } else {
+                        ko = pair_combine(m, __ldg(gp + other * N + idx), __ldg(gp + 4 * N + other * N + idx), __ldg(gp + 8 * N + other * N + idx));
+                        km = pair_combine(m, __ldg(gp + me * N + idx), __ldg(gp + 4 * N + me * N + idx), __ldg(gp + 8 * N + me * N + idx));
+                    }
                     st_async_u64(peer_recv_a + (u32)idx * 8, fmul_c(x[q], ko), peer_rcv_bar);
-                    const u64 km = pair_combine(m, __ldg(gp + me * N + idx), __ldg(gp + 4 * N + me * N + idx),
-                                                __ldg(gp + 8 * N + me * N + idx));
                     own[q] = fmul_l(x[q], km);
                 }
             } else if (ONE_LEVEL) {
@@ -312,7 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NttCfg<L, E>::T, MIN
             for (int q = 0; q < EPT; q++) own[q] = fadd_l(own[q], recv[q * T + tid]);
             ntt_inverse<L, E>(own, buf, a.twi, tid);   // (its first __syncthreads orders every thread's reads of recv / stage)
             if (tid == 0) mbar_arrive_remote(peer_free_bar);
-            if (STAGE && tid == 0) prefetch_rows(i + 1);
+            if (STAGE && tid == 0) prefetch_rows(i + (PAIR ? 2 : 1));
 #pragma unroll
             for (int q = 0; q < EPT; q++) {
                 const int idx = q * T + tid;

@@ -42,7 +42,8 @@ struct bmi_ctx {
     int split_clusters[2] = {-1, -1};   // resident 8-CTA clusters of the split kernel, single / pair rotation (queried once)
     int latency_resident = -1;          // CTAs per SM of the latency build (queried once)
     bool split_async = true;  // split kernel synchronised by mbarriers + st.async (BMI_SPLIT_ASYNC=0: cluster barriers)
-    bool tma_stage = false;  // stage GGSW rows with TMA bulk copies where shared memory allows (measured slower: off)
+    bool tma_stage = false;  // one GGSW per bit: stage its rows with TMA bulk copies where shared memory allows (measured 4-8 % slower: off)
+    bool tma_stage_pairs = true;   // pair rotation, latency build: the step's three GGSWs by TMA one step ahead (measured 2-3 % faster: on)
     // 0 auto (build chosen per launch), 1 latency build, 2 throughput build, 3 8-CTA split kernel,
     // 5 8-CTA kernel with two points per thread and warp-shuffle stages (split2.cuh; measured slower, kept for A/B)
     int pbs_mode = 0;
@@ -67,6 +68,7 @@ template <int L>
 inline size_t split2_smem(const bmi_ctx* c) { return (size_t)Split2Cfg<L>::WORDS * 8 + (((size_t)c->p.n * 2 + 15) & ~(size_t)15); }
 constexpr int kMaxSplit2L = 13;    // two points per thread: N/8 threads per CTA
 inline size_t pbs_smem_staged(const bmi_ctx* c) { return pbs_smem(c) + (size_t)2 * c->p.N * 8; }
+inline size_t pbs_smem_staged_pairs(const bmi_ctx* c) { return pbs_smem(c) + (size_t)6 * c->p.N * 8; }   // the three keys of a pair step
 
 template <int L>
 constexpr int split_convert_e() { return L <= 12 ? 2 : L == 13 ? 3 : 4; }
@@ -93,6 +95,8 @@ int setup_attrs(const bmi_ctx* c) {
         CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         if (sms <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
+        if ((int)pbs_smem_staged_pairs(c) <= kMaxSmem)
+            CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, EL, 1, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbs_smem_staged_pairs(c)));
         if (sms * TP <= kMaxSmem) CK(cudaFuncSetAttribute(pbs_cluster_kernel<L, ET, TP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sms));
         CK(cudaFuncSetAttribute(bsk_convert_kernel<L, EL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
         CK(cudaFuncSetAttribute(bsk_convert_kernel<L, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << L) * 8));
@@ -213,7 +217,10 @@ int launch_pbs(bmi_ctx* c, PbsArgs a, cudaStream_t st) {
     const size_t sm = pbs_smem(c), sms = pbs_smem_staged(c);
     if (c->pairs) {
         a.bsk_hat = c->d_bskp[latency ? 1 : 0]; a.expo = c->d_expo[latency ? 1 : 0]; a.pw = c->d_pw;
-        if (latency) pbs_cluster_kernel<L, EL, 1, true, false, true><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
+        // A/B option: the three keys of each pair step staged by TMA (latency build, where the 6N words fit)
+        if (latency && c->tma_stage_pairs && (int)pbs_smem_staged_pairs(c) <= kMaxSmem)
+            pbs_cluster_kernel<L, EL, 1, true, true, true><<<grid, NttCfg<L, EL>::T, pbs_smem_staged_pairs(c), st>>>(a);
+        else if (latency) pbs_cluster_kernel<L, EL, 1, true, false, true><<<grid, NttCfg<L, EL>::T, sm, st>>>(a);
         else pbs_cluster_kernel<L, ET, TP, true, false, true><<<grid, NttCfg<L, ET>::T, sm, st>>>(a);
         c->launches++;
         CK(cudaGetLastError());

@@ -215,7 +215,8 @@ class Engine:
         _check(lib().bmi_ctx_set_pbs_mode(self._h, mode))
 
     def set_tma_stage(self, on: bool):
-        """GGSW rows through TMA bulk copies into shared memory (off by default: measured slower than direct loads)"""
+        """GGSW rows through TMA bulk copies into shared memory, for both key kinds (defaults: on for the pair rotation's
+        latency build, where it measured 2-3 % faster; off for the one-GGSW-per-bit key, 4-8 % slower)"""
         _check(lib().bmi_ctx_set_tma_stage(self._h, int(bool(on))))
 
     @property

@@ -88,8 +88,9 @@ int64_t bmi_ctx_launch_count(const bmi_ctx* ctx);            /* kernels launched
  * only; select it BEFORE bmi_ctx_load_bsk_pairs; measured slower than 3, kept for comparison);
  * bmi_polymul_host follows the same choice */
 int bmi_ctx_set_pbs_mode(bmi_ctx* ctx, int32_t mode);
-/* 1 = bring each CMUX's GGSW rows into shared memory with a TMA bulk copy issued one CMUX ahead (where it fits);
- * 0 (default) = per-thread coalesced global loads, measured 4-8 % faster on B200 */
+/* 1 = bring each step's GGSW rows into shared memory with TMA bulk copies issued one step ahead (where they fit);
+ * 0 = per-thread coalesced global loads.  Defaults follow the measurements on B200: on for the
+ * pair rotation's latency build (2-3 % faster), off for the one-GGSW-per-bit key (4-8 % slower).  The call sets both. */
 int bmi_ctx_set_tma_stage(bmi_ctx* ctx, int32_t on);
 
 /* out[j][b] = sum_t coef[t] * vals[idx[t]][b] + konst[j], rows of k*N+1 words.
