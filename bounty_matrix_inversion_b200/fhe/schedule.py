@@ -49,9 +49,12 @@ def _dag(prog: Program):
 
 
 def default_tiers(capacity: int):
-    """launch sizes up to which a level costs about the same: the low-latency kernel's resident capacity, then whole
-    multiples of it"""
-    return [capacity * m for m in (1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 64, 128, 1 << 20)]
+    """launch sizes up to which a level costs about the same.  The steps of the measured cost curve (B200, N = 2048:
+    33 ciphertexts on the 8-CTA kernel, 74 / 148 / 222 in one / two / three waves of the latency build, 296 resident on
+    the throughput build, profiles/r2_pbs_sweep_pairs_w4.jsonl), expressed through the engine's launch capacity"""
+    wave = capacity * 296 // 33
+    return sorted({capacity, capacity * 74 // 33, capacity * 148 // 33, capacity * 222 // 33, wave}
+                  | {wave * m for m in (2, 3, 4, 6, 8, 16, 32, 64, 1 << 12)})
 
 
 def modelled_ms(prog: Program, capacity: int, world: int = 1) -> float:
