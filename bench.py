@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer pass (profile runs of the full 4,096-pair workload)")
-    ap.add_argument("--time-budget", type=float, default=560.0, help="seconds the whole run aims to stay within: the host-buffer "
+    ap.add_argument("--time-budget", type=float, default=540.0, help="seconds the whole run aims to stay within: the host-buffer "
                     "(e2e) pass repeats the step as often as the remaining time allows (at least twice, at most --steps)")
     ap.add_argument("--inversion", default="auto", help="also time one encrypted inversion: 2 | 3 | 4 (low precision), a "
                                                        "compiled program in tests/golden (e.g. inv3_medium, inv4_high_prefix), "
@@ -328,8 +328,8 @@ def run_microbench(args, fhe, PR, torch, dist, local, rank, world):
         circuits[op]._executor.profile = None
 
     # the host-buffer pass repeats the same step; how often is bounded by the time the run has left (the inversion and
-    # the CPU sample still need about 100 s), identically on every rank
-    left = args.time_budget - (time.time() - args.t_start) - 100.0
+    # the CPU sample still need about 130 s), identically on every rank
+    left = args.time_budget - (time.time() - args.t_start) - 130.0
     e2e_steps = 1 if args.no_e2e else int(max(2, min(args.steps, left / max(dev_ms / args.steps * 1e-3, 1e-3))))
     if world > 1:
         agreed = torch.tensor([e2e_steps], dtype=torch.int64, device="cuda")
