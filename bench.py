@@ -101,13 +101,17 @@ def cpu_context(progs):
         from bounty_matrix_inversion_b200 import native, params as PR
         from oracle import oracle as orc
         orc.use_native_build()
+        by_set = {}                                   # circuits that selected the same numbers share one key set
         for op in OPS:
             prog = progs[op][0]
             prm = PR.for_width(prog.width, prog.nu2, bsk_group=2)
-            pk = native.ClientKeys(prm, seed=11, pairs=True)
-            sk = native.ClientKeys(prm, seed=11, pairs=False)
-            _CPU_CTX[op] = (prm, pk, orc.Fast(prm, None, pk.ksk, bskp=pk.bskp), orc.Fast(prm, sk.bsk, sk.ksk),
-                            prog.lut_polynomials(prm.N)[:1])
+            sig = (prm.n, prm.k, prm.N, prm.bsk_bl, prm.bsk_l, prm.ksk_bl, prm.ksk_l, prm.lwe_sigma, prm.glwe_sigma)
+            if sig not in by_set:
+                pk = native.ClientKeys(prm, seed=11, pairs=True)
+                sk = native.ClientKeys(prm, seed=11, pairs=False)
+                by_set[sig] = (pk, orc.Fast(prm, None, pk.ksk, bskp=pk.bskp), orc.Fast(prm, sk.bsk, sk.ksk))
+            pk, fast_pairs, fast_single = by_set[sig]
+            _CPU_CTX[op] = (prm, pk, fast_pairs, fast_single, prog.lut_polynomials(prm.N)[:1])
     return _CPU_CTX
 
 
